@@ -1,0 +1,317 @@
+"""The compiled program object of ``cuda`` mode.
+
+``CudaProgram`` plays the role of the ``CompiledSDFG`` that ``sdfg.compile()`` hands to the reference
+driver (``stencilflow/run_program.py:123,164-172``; ``dace/dace/codegen/compiled_sdfg.py:269-294``):
+it is called with keyword arguments ``<input>_host=ndarray``, ``<scalar>=value`` and
+``<output>_host=ndarray`` (un-suffixed names are accepted too, as the reference's CPU program takes
+them, ``run_program.py:186-192``); outputs are caller-allocated and written in place.
+
+Underneath: front end -> operator 5-tuples -> planner -> generated sm_100a CUDA C++ -> NVRTC cubin
+(cached under ``.sfcache/``) -> module -> launches on one stream, all through ``libsfb200.so``.
+"""
+
+import ctypes
+import hashlib
+import json
+import os
+import time
+
+import numpy as np
+
+from . import planner as _planner
+from . import runtime as rt
+from .kernel_chain_graph import KernelChainGraph
+from .log_level import LogLevel
+from .stencil_op import make_program
+
+NVRTC_OPTIONS = ["-arch=sm_100a", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
+
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def cache_root():
+    return os.environ.get("SFB200_CACHE", os.path.join(_REPO_ROOT, ".sfcache"))
+
+
+def compile_cached(name, source, options=None):
+    """Generated CUDA C++ -> cubin bytes, cached on disk by content hash (the counterpart of
+    ``.dacecache/<name>/`` and ``-use-cached-sdfg``, ``stencilflow/run_program.py:69-73``).
+    Returns (cubin, directory, was_cached)."""
+    options = [o for o in (options or NVRTC_OPTIONS) if o != "--use_fast_math=false"]
+    key = hashlib.sha1((source + "\0" + " ".join(options)).encode()).hexdigest()[:16]
+    directory = os.path.join(cache_root(), "{}-{}".format(name, key))
+    cubin_path = os.path.join(directory, "kernel.cubin")
+    src_path = os.path.join(directory, "kernel.cu")
+    if os.path.isfile(cubin_path) and os.path.isfile(src_path):
+        with open(cubin_path, "rb") as f:
+            return f.read(), directory, True
+    os.makedirs(directory, exist_ok=True)
+    with open(src_path, "w") as f:
+        f.write(source)
+    image, log = rt.compile_source(source, src_path, options)
+    tmp = cubin_path + ".tmp{}".format(os.getpid())
+    with open(tmp, "wb") as f:
+        f.write(image)
+    os.replace(tmp, cubin_path)
+    if log.strip():
+        with open(os.path.join(directory, "nvrtc.log"), "w") as f:
+            f.write(log)
+    return image, directory, False
+
+
+class DeviceBuffer:
+    def __init__(self, name, nbytes, dptr):
+        self.name = name
+        self.nbytes = nbytes
+        self.dptr = dptr
+
+
+class CudaProgram:
+    def __init__(self, stencil_file=None, chain=None, log_level=LogLevel.NO_LOG, device=None,
+                 plan_options=None, specialize_scalars=None, synthetic_reads=None,
+                 allocate=True, slab=None):
+        """``slab``: None for a whole-domain program, or a :class:`distributed.Slab` describing the
+        part of the outermost dimension this process owns (multi-GPU)."""
+        if chain is None:
+            chain = KernelChainGraph(stencil_file, log_level=log_level)
+        self.chain = chain
+        self.name = chain.name.replace(".", "_")
+        self.program = make_program(chain)
+        self.slab = slab
+        self.synthetic_reads = synthetic_reads
+        self.plan = _planner.plan_program(self.program, options=plan_options,
+                                          specialize=specialize_scalars)
+        self.lowered = self.plan.lowered
+        self.image, self.cache_dir, self.was_cached = compile_cached(self.name, self.lowered.source)
+        with open(os.path.join(self.cache_dir, "plan.json"), "w") as f:
+            json.dump(self.plan.describe(), f, indent=1)
+        self.rt = None
+        self.module = None
+        self.functions = {}
+        self.buffers = {}          # field -> DeviceBuffer
+        self._owned = []
+        self._packs = None
+        self._graph = None
+        self.scalar_values = {}
+        self.launch_count = 0
+        if allocate:
+            self.load(device)
+
+    # ------------------------------------------------------------------ device set-up
+    def load(self, device=None):
+        self.rt = rt.Runtime.get(device)
+        self.module = self.rt.module_load(self.image)
+        for name, k in self.lowered.kernels.items():
+            fn = self.rt.get_function(self.module, name)
+            self.functions[name] = fn
+        for l in self.lowered.launches:
+            if l.smem > 48 * 1024:
+                self.rt.set_max_dynamic_smem(self.functions[l.kernel], l.smem)
+        self._allocate()
+
+    def local_shape(self, field):
+        """Shape of a field's device buffer (slab extent + halos along the slab axis)."""
+        f = self.program.fields[field]
+        if self.slab is None or self.lowered.slab_axis is None:
+            return f.shape
+        it = "ijk"[self.lowered.slab_axis]
+        if it not in f.dims:
+            return f.shape
+        shape = list(f.shape)
+        shape[f.dims.index(it)] = self.slab.alloc_end - self.slab.alloc_begin
+        return tuple(shape)
+
+    def _allocate(self):
+        fields = self.program.fields
+        assign = self.plan.buffer_assignment()        # materialised field -> storage id
+        storage = {}
+        for name, sid in assign.items():
+            f = fields[name]
+            nbytes = int(np.prod(self.local_shape(name))) * f.data_type.bytes
+            storage[sid] = max(storage.get(sid, 0), nbytes)
+        ptrs = {}
+        for sid, nbytes in storage.items():
+            ptrs[sid] = self.rt.malloc(nbytes)
+            self._owned.append(ptrs[sid])
+        for name, sid in assign.items():
+            self.buffers[name] = DeviceBuffer(name, storage[sid], ptrs[sid])
+        self.device_bytes = sum(storage.values())
+
+    def close(self):
+        if self.rt is None:
+            return
+        if self._graph is not None:
+            self.rt.graph_destroy(self._graph)
+            self._graph = None
+        for p in self._owned:
+            self.rt.free(p)
+        self._owned = []
+        self.buffers = {}
+        if self.module is not None:
+            self.rt.module_unload(self.module)
+            self.module = None
+
+    # ------------------------------------------------------------------ execution
+    def _slab_range(self):
+        axis = self.lowered.slab_axis
+        if axis is None:
+            return 0, 0, 1
+        n = self.program.shape3[axis]
+        if self.slab is None:
+            return 0, 0, n
+        return self.slab.alloc_begin, self.slab.begin, self.slab.end
+
+    def set_scalars(self, values):
+        for k, v in values.items():
+            self.scalar_values[k] = v
+        self._packs = None
+        if self._graph is not None:
+            self.rt.graph_destroy(self._graph)
+            self._graph = None
+
+    def _build_packs(self):
+        packs = []
+        s_base, s_begin, s_end = self._slab_range()
+        for l in self.lowered.launches:
+            vals = []
+            keep = []
+            b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
+            for a in l.args:
+                if a[0] == "buf":
+                    vals.append(ctypes.c_void_p(self.buffers[a[1]].dptr))
+                elif a[0] == "scalar":
+                    dt, name = a[1], a[2]
+                    if name not in self.scalar_values:
+                        raise KeyError("scalar input {} was not provided".format(name))
+                    vals.append(np.ctypeslib.as_ctypes_type(dt.type)(self.scalar_values[name]))
+                elif a[0] == "slab":
+                    vals += [ctypes.c_int(s_base), ctypes.c_int(b0), ctypes.c_int(e0)]
+                elif a[0] == "int":
+                    vals.append(ctypes.c_int(a[1]))
+                elif a[0] == "tmap":
+                    spec = a[1]
+                    buf = self.buffers[spec["field"]]
+                    shape = self.local_shape(spec["field"])
+                    dt = self.program.fields[spec["field"]].data_type
+                    dims = list(reversed(shape))
+                    strides = []
+                    acc = dt.bytes
+                    for d in dims[:-1]:
+                        acc *= d
+                        strides.append(acc)
+                    box = list(spec["box"])
+                    vals.append(self.rt.tensor_map(buf.dptr, dt, dims, strides, box))
+                else:
+                    raise ValueError(a)
+            pack = rt.pack_params(vals)
+            packs.append((l, self.functions[l.kernel], l.grid_fn(b0, e0), pack))
+        self._packs = packs
+
+    def execute(self, stream=None):
+        """Enqueue every launch of the plan (asynchronous)."""
+        if self._packs is None:
+            self._build_packs()
+        for l, fn, grid, pack in self._packs:
+            self.rt.launch(fn, grid, l.block, l.smem, pack.array, stream)
+        self.launch_count += len(self._packs)
+
+    def execute_graph(self):
+        """Same as :meth:`execute` through a captured CUDA graph (launch-bound programs)."""
+        if self._graph is None:
+            self.rt.graph_begin()
+            try:
+                self.execute()
+            finally:
+                self._graph = self.rt.graph_end()
+        else:
+            self.launch_count += len(self._packs)
+        self.rt.graph_launch(self._graph)
+
+    @property
+    def launches_per_execution(self):
+        return len(self.lowered.launches)
+
+    def upload(self, name, array):
+        f = self.program.fields[name]
+        shape = self.local_shape(name)
+        n = int(np.prod(shape))
+        arr = np.asarray(array)
+        if arr.dtype != f.data_type.type:
+            arr = arr.astype(f.data_type.type)
+        if arr.size < n:
+            raise ValueError("input {} has {} elements, the program needs {}".format(name, arr.size, n))
+        if arr.shape != tuple(shape):
+            # the reference hands lower-dimensional inputs over at the full program shape and embedded
+            # lists flat; the program reads the first prod(shape) elements (helper.py:162-217)
+            arr = np.ascontiguousarray(arr).ravel()[:n]
+        arr = np.ascontiguousarray(arr)
+        self.rt.h2d(self.buffers[name].dptr, arr, nbytes=n * f.data_type.bytes)
+        self.rt.stream_synchronize()
+
+    def download(self, name, out=None):
+        f = self.program.fields[name]
+        shape = self.local_shape(name)
+        if out is None:
+            out = np.empty(shape, dtype=f.data_type.type)
+        n = int(np.prod(shape))
+        if out.size != n or out.dtype != f.data_type.type or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("output array for {} must be C-contiguous {} of {} elements".format(
+                name, f.data_type, n))
+        self.rt.d2h(out, self.buffers[name].dptr, nbytes=n * f.data_type.bytes)
+        self.rt.stream_synchronize()
+        return out
+
+    def _split_call_args(self, kwargs):
+        arrays, scalars = {}, {}
+        for key, val in kwargs.items():
+            name = key[:-5] if key.endswith("_host") and key[:-5] in self.program.fields else key
+            if name not in self.program.fields:
+                raise KeyError("unknown program argument {}".format(key))
+            if self.program.fields[name].is_scalar:
+                scalars[name] = val
+            else:
+                arrays[name] = val
+        return arrays, scalars
+
+    def __call__(self, **kwargs):
+        """Run once with host arrays: copy inputs in, execute, copy outputs back in place."""
+        arrays, scalars = self._split_call_args(kwargs)
+        fields = self.program.fields
+        for name, f in fields.items():
+            if f.kind == "input" and not f.is_scalar:
+                if self.synthetic_reads is not None:
+                    self.rt.fill_constant(self.buffers[name].dptr, int(np.prod(self.local_shape(name))),
+                                          f.data_type, self.synthetic_reads)
+                elif name in arrays:
+                    self.upload(name, arrays[name])
+                else:
+                    raise KeyError("input array {} was not provided".format(name))
+        need = [n for n, f in fields.items() if f.is_scalar]
+        missing = [n for n in need if n not in scalars and n not in self.scalar_values]
+        if missing:
+            raise KeyError("scalar input(s) {} were not provided".format(missing))
+        if scalars:
+            self.set_scalars(scalars)
+        self.execute()
+        for name in self.program.outputs:
+            if name in arrays:
+                self.download(name, arrays[name])
+        self.rt.stream_synchronize()
+
+    def time_execution(self, repetitions=10, warmup=3, graph=False):
+        """Device time (ms, list) of ``repetitions`` executions, CUDA events on the launch stream."""
+        run = self.execute_graph if graph else self.execute
+        for _ in range(warmup):
+            run()
+        self.rt.stream_synchronize()
+        times = []
+        e0, e1 = self.rt.event_create(), self.rt.event_create()
+        for _ in range(repetitions):
+            self.rt.event_record(e0)
+            run()
+            self.rt.event_record(e1)
+            self.rt.event_synchronize(e1)
+            times.append(self.rt.elapsed_ms(e0, e1))
+        self.rt.event_destroy(e0)
+        self.rt.event_destroy(e1)
+        return times

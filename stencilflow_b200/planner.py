@@ -1,0 +1,161 @@
+"""Fusion-depth and tile planner: decides how the operator DAG is cut into passes over HBM.
+
+This replaces the reference's buffer-placement optimizer (``stencilflow/optimizer.py:73-307``), which
+greedily moves FPGA delay/window buffers between fast (on-chip) and slow (off-chip) memory under a
+size or communication-volume bound.  On a GPU the same trade-off reads: a field that stays *inside* a
+pass lives in registers/shared memory (fast memory) and costs no HBM traffic; a field that crosses a
+pass boundary is written to and re-read from HBM (slow memory).  The planner therefore
+
+1. walks the operators in topological order and grows a *pass* (fusion group) while the group is
+   streamable (see :mod:`lower_stream` for the conditions), its fusion depth stays within
+   ``max_depth`` and its tile fits the shared-memory/register budget (227 KB per CTA, 64 K registers
+   per SM);
+2. lowers each pass with the streamed template, or -- for operators the template cannot express
+   (copy boundaries, far taps, lower-dimensional array inputs, mixed boundary values ...) -- with the
+   general one-operator kernel;
+3. assigns HBM storage to the fields that cross pass boundaries, reusing the storage of dead
+   intermediates (the reference keeps every transient alive, ``stencilflow/sdfg_generator.py:626-630``;
+   results are identical, the footprint is what makes 2048^3 x 64 operators fit).
+
+``Plan.describe()`` is the inspectable record of these decisions (written to ``plan.json`` next to
+the generated source).
+"""
+
+import os
+from typing import Dict, List, Optional
+
+from . import lower_cuda
+from .stencil_op import StencilProgram
+
+
+class PlanOptions:
+    """Knobs, all overridable through ``SFB200_*`` environment variables."""
+
+    def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
+                 prefetch=None):
+        env = os.environ
+        self.fuse = (env.get("SFB200_FUSE", "1") != "0") if fuse is None else fuse
+        self.max_depth = int(env.get("SFB200_MAX_DEPTH", "0")) if max_depth is None else max_depth
+        self.rows_per_thread = int(env.get("SFB200_ROWS", "0")) if rows_per_thread is None else rows_per_thread
+        self.warps = int(env.get("SFB200_WARPS", "0")) if warps is None else warps
+        self.chunk = int(env.get("SFB200_CHUNK", "0")) if chunk is None else chunk
+        self.prefetch = int(env.get("SFB200_PREFETCH", "0")) if prefetch is None else prefetch
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+
+class Plan:
+    def __init__(self, program: StencilProgram, lowered, passes, options):
+        self.program = program
+        self.lowered = lowered
+        self.passes = passes          # list of dicts: {"ops": [...], "family": ..., ...}
+        self.options = options
+
+    def materialized_fields(self) -> List[str]:
+        names = []
+        for l in self.lowered.launches:
+            for f in list(l.reads) + list(l.writes):
+                if f not in names and not self.program.fields[f].is_scalar:
+                    names.append(f)
+        for name, f in self.program.fields.items():
+            if f.kind in ("input", "output") and not f.is_scalar and name not in names:
+                names.append(name)
+        return names
+
+    def buffer_assignment(self) -> Dict[str, int]:
+        """field -> storage id.  Inputs and outputs own their storage; intermediates that cross
+        pass boundaries share storage once dead (equal byte size only)."""
+        fields = self.program.fields
+        launches = self.lowered.launches
+        first_write, last_read = {}, {}
+        for idx, l in enumerate(launches):
+            for f in l.writes:
+                first_write.setdefault(f, idx)
+            for f in l.reads:
+                last_read[f] = idx
+        assign, next_id = {}, 0
+        free_pool = []            # (nbytes, storage id)
+        busy = []                 # (last read index, nbytes, storage id)
+        for name in self.materialized_fields():
+            if fields[name].kind != "intermediate":
+                assign[name] = next_id
+                next_id += 1
+        for idx, l in enumerate(launches):
+            still = []
+            for (lr, nb, sid) in busy:
+                if lr < idx:
+                    free_pool.append((nb, sid))
+                else:
+                    still.append((lr, nb, sid))
+            busy = still
+            for f in l.writes:
+                if f in assign:
+                    continue
+                nb = fields[f].nbytes
+                sid = None
+                for k, (pnb, psid) in enumerate(free_pool):
+                    if pnb == nb:
+                        sid = psid
+                        free_pool.pop(k)
+                        break
+                if sid is None:
+                    sid = next_id
+                    next_id += 1
+                assign[f] = sid
+                busy.append((last_read.get(f, idx), nb, sid))
+        return assign
+
+    def algorithmic_bytes(self) -> int:
+        return self.lowered.algorithmic_bytes()
+
+    def cell_updates(self) -> int:
+        return len(self.program.ops) * self.program.cells
+
+    def describe(self):
+        fields = self.program.fields
+        return {
+            "program": self.program.name,
+            "shape": list(self.program.shape),
+            "operators": len(self.program.ops),
+            "cell_updates": self.cell_updates(),
+            "options": self.options.as_dict(),
+            "passes": [
+                {
+                    "family": l.family, "kernel": l.kernel, "ops": l.ops, "reads": l.reads,
+                    "writes": l.writes, "block": list(l.block), "smem": l.smem,
+                    "algorithmic_bytes": sum(fields[f].nbytes for f in l.reads) +
+                    sum(fields[f].nbytes for f in l.writes),
+                    "info": {k: v for k, v in l.info.items() if not callable(v)},
+                } for l in self.lowered.launches
+            ],
+            "algorithmic_bytes": self.algorithmic_bytes(),
+            "storage": self.buffer_assignment(),
+        }
+
+
+def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
+                 specialize=None) -> Plan:
+    options = options or PlanOptions()
+    lowered = lower_cuda.LoweredProgram(program)
+    passes = []
+    groups = None
+    if options.fuse:
+        try:
+            from . import lower_stream
+        except ImportError:
+            lower_stream = None
+        if lower_stream is not None:
+            groups = lower_stream.partition(program, options)
+    if groups is None:
+        groups = [("general", [op]) for op in program.ops]
+    for family, ops in groups:
+        if family == "general":
+            for op in ops:
+                lower_cuda.lower_general_op(lowered, op, specialize)
+                passes.append({"family": "general", "ops": [op.name]})
+        else:
+            from . import lower_stream
+            lower_stream.lower_group(lowered, ops, options, specialize)
+            passes.append({"family": "streamed", "ops": [op.name for op in ops]})
+    return Plan(program, lowered, passes, options)

@@ -1,0 +1,68 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PROGRAMS = os.path.join(ROOT, "tests", "programs")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def program_path(name):
+    return os.path.join(PROGRAMS, name + ".json")
+
+
+def all_programs():
+    return sorted(os.path.splitext(f)[0] for f in os.listdir(PROGRAMS) if f.endswith(".json"))
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """libsfb200.so, built on demand (nvcc cross-compiles without a GPU)."""
+    from stencilflow_b200 import build
+    build.build_native()
+    from stencilflow_b200 import runtime
+    return runtime.load_library()
+
+
+# programs with "shrink" boundaries: width of the border whose content is junk by definition
+# (run_program's -halo, reference stencilflow/run_program.py:202-209)
+HALO = {
+    "hdiff_24x28x16": 2,
+    "hdiff_16x20x8_f64": 2,
+    "jacobi2d_96x128_6itr_shrink_f64": 6,
+    "jacobi3d_24x20x40_4itr_shrink_f64": 4,
+}
+
+# value ranges of the random test inputs; hdiff subtracts a small correction from `inp`, so its
+# inputs are kept away from zero to make a *relative* error bound meaningful
+INPUT_RANGES = {
+    "hdiff_24x28x16": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
+    "hdiff_16x20x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
+}
+
+
+def random_inputs(name, seed=7):
+    """Seeded random inputs for a test program: {input name: ndarray or numpy scalar}."""
+    import numpy as np
+    from oracle import reference_numpy as rn
+    prog = rn.load_program(program_path(name))
+    info = rn.ProgramInfo(prog)
+    rng = np.random.default_rng(seed)
+    inputs = {}
+    for field in info.inputs:
+        shape = info.field_shape(field)
+        dt = info.field_type(field)
+        lo, hi = INPUT_RANGES.get(name, {}).get(field, (0.0, 1.0))
+        if len(shape) == 0:
+            inputs[field] = dt(rng.uniform(0.5, 1.5))
+        else:
+            inputs[field] = rng.uniform(lo, hi, size=shape).astype(dt)
+    return inputs
