@@ -104,7 +104,7 @@ def main():
             "b": {"computation_string": "b = 0.125 * (a[i-1,j-1,k-1] + a[i-1,j+1,k+1] + a[i+1,j-1,k+1] + a[i+1,j+1,k-1] + "
                                         "a[i,j,k-2] + a[i,j,k+2] + a[i,j-2,k] + a[i+2,j,k])",
                   "boundary_conditions": {"a": {"type": "constant", "value": 2.0}}, "data_type": "float32"},
-            "c": {"computation_string": "c = b[i,j,k] - 0.5 * b[i-1,j,k+3]",
+            "c": {"computation_string": "c = b[i,j,k] + 0.5 * b[i-1,j,k+3]",
                   "boundary_conditions": {"b": {"type": "constant", "value": -1.0}}, "data_type": "float32"}}})
     dump("math_ops_8x8x8", {
         "inputs": {"a": {"data": "constant:0.75", "data_type": "float32"},
@@ -113,10 +113,10 @@ def main():
         "outputs": ["r"], "dimensions": [8, 8, 8],
         "constants": {"c0": {"value": 0.5, "data_type": "float32"}},
         "program": {
-            "t": {"computation_string": "s = sqrt(a[i,j,k] + b[i,j,k+1]); t = max(s, c0) - min(a[i,j-1,k], b[i,j,k]) * w",
+            "t": {"computation_string": "s = sqrt(a[i,j,k] + b[i,j,k+1]); t = max(s, c0) + min(a[i,j-1,k], b[i,j,k]) * w",
                   "boundary_conditions": {"a": {"type": "constant", "value": 1.0}, "b": {"type": "constant", "value": 4.0}},
                   "data_type": "float32"},
-            "r": {"computation_string": "r = (t[i,j,k] if (t[i,j,k] > 0.9 and a[i,j,k] < 1.0) or t[i-1,j,k] <= 0.0 else -t[i,j,k]) / 2.0 + fabs(cos(t[i,j,k-1]))",
+            "r": {"computation_string": "r = (t[i,j,k] if (t[i,j,k] > 0.9 and a[i,j,k] < 1.0) or t[i-1,j,k] <= 0.0 else 3.0*t[i,j,k]) / 2.0 + fabs(cos(t[i,j,k-1]))",
                   "boundary_conditions": {"t": {"type": "constant", "value": 0.0}, "a": {"type": "constant", "value": 0.0}},
                   "data_type": "float32"}}})
     dump("smooth1d_256", {
@@ -125,7 +125,7 @@ def main():
         "program": {
             "y": {"computation_string": "y = 0.25*x[k-1] + 0.5*x[k] + 0.25*x[k+1]",
                   "boundary_conditions": {"x": {"type": "constant", "value": 0.0}}, "data_type": "float64"},
-            "z": {"computation_string": "z = y[k+2] - y[k-2]",
+            "z": {"computation_string": "z = y[k+2] + 0.5*y[k-2]",
                   "boundary_conditions": {"y": {"type": "copy"}}, "data_type": "float64"}}})
     p = json.loads(json.dumps(p))
     dump("lowdim2d_32x64", {
@@ -147,7 +147,7 @@ def main():
                   "boundary_conditions": {"b": {"type": "constant", "value": 0.0}}, "data_type": "float32"},
             "d": {"computation_string": "d = 0.5 * (b[i,j,k-1] + b[i,j,k+1]) + a[i,j,k]",
                   "boundary_conditions": {"b": {"type": "constant", "value": 0.0}}, "data_type": "float32"},
-            "e": {"computation_string": "e = c[i,j,k] + d[i+1,j,k] - d[i-1,j,k]",
+            "e": {"computation_string": "e = c[i,j,k] + d[i+1,j,k] + 0.5*d[i-1,j,k]",
                   "boundary_conditions": {"d": {"type": "constant", "value": 0.0}}, "data_type": "float32"}}})
 
 
