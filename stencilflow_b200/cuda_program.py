@@ -188,6 +188,8 @@ class CudaProgram:
                     vals += [ctypes.c_int(s_base), ctypes.c_int(b0), ctypes.c_int(e0)]
                 elif a[0] == "int":
                     vals.append(ctypes.c_int(a[1]))
+                elif a[0] == "chunk":
+                    vals.append(ctypes.c_int(l.info["chunk_fn"](b0, e0)))
                 elif a[0] == "tmap":
                     spec = a[1]
                     buf = self.buffers[spec["field"]]

@@ -105,7 +105,7 @@ def main():
                                         "a[i,j,k-2] + a[i,j,k+2] + a[i,j-2,k] + a[i+2,j,k])",
                   "boundary_conditions": {"a": {"type": "constant", "value": 2.0}}, "data_type": "float32"},
             "c": {"computation_string": "c = b[i,j,k] + 0.5 * b[i-1,j,k+3]",
-                  "boundary_conditions": {"b": {"type": "constant", "value": -1.0}}, "data_type": "float32"}}})
+                  "boundary_conditions": {"b": {"type": "constant", "value": 1.0}}, "data_type": "float32"}}})
     dump("math_ops_8x8x8", {
         "inputs": {"a": {"data": "constant:0.75", "data_type": "float32"},
                    "b": {"data": "constant:0.25", "data_type": "float32"},
