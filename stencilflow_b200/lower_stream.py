@@ -36,7 +36,7 @@ from .lower_cuda import (KernelSpec, LaunchSpec, LoweredProgram, _MATH_F32, _MAT
 from .stencil_op import JUNK_VAL, StencilOp, StencilProgram
 
 SMEM_LIMIT = 227 * 1024
-REG_BUDGET = 150          # estimated window registers per thread the planner accepts
+REG_BUDGET = 110          # estimated window registers per thread the planner accepts
 
 STREAM_PRELUDE = r"""
 // ---- streamed-kernel support (TMA + mbarrier, sm_100a) ----
@@ -106,6 +106,7 @@ class _FieldInfo:
         self.stored = False
         self.consumed = False
         self.back = 0                 # planes of history a chunk needs before its first output plane
+        self.fwd = 0                  # planes beyond the last output plane of a chunk that are read
         self.need = [0, 0, 0, 0]      # halo (row lo, row hi, col lo, col hi) this field must be valid on
 
 
@@ -219,6 +220,7 @@ class GroupAnalysis:
         for op in reversed(self.ops):
             for (field, d, dj, dk) in self.taps[op.name]:
                 f[field].back = max(f[field].back, f[op.name].back + max(0, -d))
+                f[field].fwd = max(f[field].fwd, f[op.name].fwd + max(0, d))
 
     def _halos(self):
         f = self.fields
@@ -737,32 +739,101 @@ def choose_geometry(program, ops, options) -> Optional[Tuple[GroupAnalysis, Geom
         return None
 
 
-def default_max_depth(program):
-    return 4
+# Cost model of the planner (seconds).  Calibrated on B200 (profiles/sweep_depth_rows_r01.txt):
+# a streamed pass costs max(HBM time of its algorithmic bytes, issue time of the cells it computes
+# including the redundant halo cells).
+HBM_BYTES_PER_S = 6.4e12
+UPDATES_PER_S = {4: 1.9e12, 8: 0.9e12}      # computed cell updates per second, by element size
+GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
+
+
+def _tile_efficiency(ana, geo):
+    if ana.ndim == 3:
+        return (geo.BJ * geo.BK) / float(geo.TR * geo.TC)
+    return geo.BK / float(geo.TC)
+
+
+def group_cost(program, ops, options):
+    """Estimated time of one streamed pass over ``ops`` (None if the group cannot stream)."""
+    chosen = choose_geometry(program, ops, options)
+    if chosen is None:
+        return None
+    ana, geo = chosen
+    fields = program.fields
+    nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields)
+    nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
+    eff = _tile_efficiency(ana, geo)
+    used = min(1.0, program.shape[-1] / float(geo.BK)) if program.shape[-1] < geo.BK else 1.0
+    t_mem = nbytes / HBM_BYTES_PER_S
+    t_cmp = program.cells * len(ops) / (eff * used) / UPDATES_PER_S[ana.dtype.bytes]
+    return max(t_mem, t_cmp) + 5e-6
+
+
+def general_cost(program, op):
+    fields = program.fields
+    nbytes = fields[op.name].nbytes + sum(fields[f].nbytes for f in op.accesses)
+    return nbytes / (HBM_BYTES_PER_S * GENERAL_EFFICIENCY) + 5e-6
 
 
 def partition(program: StencilProgram, options):
-    """Greedy grouping of the topologically ordered operators into passes."""
-    groups = []
+    """Cut the topologically ordered operators into passes minimising the modelled run time
+    (dynamic programme over contiguous groups of at most ``max_depth`` operators)."""
     ops = list(program.ops)
-    max_depth = options.max_depth or default_max_depth(program)
-    idx = 0
-    while idx < len(ops):
-        best = None
-        for end in range(idx + 1, min(len(ops), idx + max_depth) + 1):
-            cand = ops[idx:end]
-            if choose_geometry(program, cand, options) is not None:
-                best = cand
-            else:
-                # a dead operator only becomes live once its consumer joins the group: keep growing
+    n = len(ops)
+    max_depth = options.max_depth or 8
+    best = [0.0] + [None] * n          # best[k]: cost of the first k operators
+    choice = [None] * (n + 1)
+    cache = {}
+    for end in range(1, n + 1):
+        for start in range(max(0, end - max_depth), end):
+            group = ops[start:end]
+            key = None
+            if len(group) > 1 or True:
+                # structurally identical groups (Jacobi chains) share one estimate
+                key = tuple((tuple(sorted((f, tuple(op.offsets3(f))) for f in op.accesses)) if False else
+                             (len(op.accesses), str(sorted(op.offsets3(f) for f in op.accesses)),
+                              str(op.boundary_conditions.values())))
+                            for op in group) + (len(group),)
+            cost = cache.get(key) if key in cache and _chain_like(group) else None
+            if cost is None:
+                cost = group_cost(program, group, options)
+                if _chain_like(group):
+                    cache[key] = cost if cost is not None else -1.0
+            elif cost < 0:
+                cost = None
+            family = "streamed"
+            if cost is None:
+                if len(group) > 1:
+                    continue
+                cost, family = general_cost(program, group[0]), "general"
+            if best[start] is None:
                 continue
-        if best is None:
-            groups.append(("general", [ops[idx]]))
-            idx += 1
-        else:
-            groups.append(("streamed", best))
-            idx += len(best)
+            total = best[start] + cost
+            if best[end] is None or total < best[end] - 1e-12:
+                best[end] = total
+                choice[end] = (start, family)
+    groups = []
+    end = n
+    while end > 0:
+        start, family = choice[end]
+        groups.append((family, ops[start:end]))
+        end = start
+    groups.reverse()
     return groups
+
+
+def _chain_like(group):
+    """True when every operator reads exactly one array field: the previous operator's result
+    (or the group's single input) -- the case where cost estimates can be shared."""
+    prev = None
+    for op in group:
+        if len(op.accesses) != 1:
+            return False
+        (field,) = op.accesses.keys()
+        if prev is not None and field != prev:
+            return False
+        prev = op.name
+    return True
 
 
 def choose_chunk(n_stream, tiles, overhead, sms=148):
@@ -816,6 +887,8 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "stream_overhead_planes": overhead,
                               "back": max(i.back for i in ana.fields.values()),
+                              "reach": {i.name: (i.back, i.fwd) for i in ana.ext_fields},
+                              "tile_efficiency": _tile_efficiency(ana, geo),
                               "fwd": ana.max_lag,
                               "chunk_fn": chunk_for})
     lowered.launches.append(launch)

@@ -79,13 +79,16 @@ class StencilOp:
 
     def offsets3(self, field) -> List[Tuple[Optional[int], ...]]:
         """Offsets of ``field`` as (di, dj, dk) with None for dimensions it lacks."""
-        mask, offs = self.accesses[field]
-        present = [it for it, m in zip(self.iterators, mask) if m]
-        out = []
-        for off in offs:
-            by = dict(zip(present, off))
-            out.append(tuple(by.get(it) for it in ex.ITERATORS))
-        return out
+        cache = self.__dict__.setdefault("_offsets3", {})
+        if field not in cache:
+            mask, offs = self.accesses[field]
+            present = [it for it, m in zip(self.iterators, mask) if m]
+            out = []
+            for off in offs:
+                by = dict(zip(present, off))
+                out.append(tuple(by.get(it) for it in ("i", "j", "k")))
+            cache[field] = out
+        return list(cache[field])
 
     def extent(self, it):
         """(min, max) offset over all array accesses along iterator ``it`` (0,0 if none)."""

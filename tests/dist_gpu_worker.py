@@ -1,0 +1,64 @@
+"""One rank of the multi-GPU parity test (launched by torchrun from tests/test_distributed_gpu.py):
+slab-decomposed execution with NVLink halo pushes vs the oracle and vs the single-GPU result."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import reference_numpy as rn  # noqa: E402
+from stencilflow_b200 import distributed  # noqa: E402
+from stencilflow_b200.cuda_program import CudaProgram  # noqa: E402
+from stencilflow_b200.planner import PlanOptions  # noqa: E402
+import conftest  # noqa: E402
+
+
+def main():
+    name, fuse = sys.argv[1], sys.argv[2] == "1"
+    comm = distributed.TorchComm("gloo")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    path = conftest.program_path(name)
+    inputs = conftest.random_inputs(name, seed=21)
+    opts = PlanOptions(fuse=fuse)
+    prog = distributed.SlabProgram(path, comm, device=local_rank, plan_options=opts)
+    scalars = {k: v for k, v in inputs.items() if getattr(v, "ndim", 0) == 0}
+    if scalars:
+        prog.set_scalars(scalars)
+    for k, v in inputs.items():
+        if getattr(v, "ndim", 0) > 0:
+            prog.upload_global(k, v)
+    for _ in range(3):                      # repeated executions exercise the flag sequence numbers
+        prog.execute()
+    prog.rt.stream_synchronize()
+    expected = rn.run_reference(path, inputs)
+    h = conftest.HALO.get(name, 0)
+    ok = True
+    report = {}
+    for out in prog.program.outputs:
+        full = prog.gather(out)
+        tol = 1e-12 if full.dtype == np.float64 else 1e-5
+        err = rn.max_relative_error(rn.trim_halo(expected[out], h), rn.trim_halo(full, h))
+        report[out] = err
+        ok = ok and err <= tol
+        if comm.rank == 0:
+            single = CudaProgram(path, device=local_rank, plan_options=opts)
+            outs = {o + "_host": np.zeros_like(expected[o]) for o in prog.program.outputs}
+            args = {(k + "_host" if getattr(v, "ndim", 0) > 0 else k): v for k, v in inputs.items()}
+            single(**args, **outs)
+            single.close()
+            same = np.array_equal(rn.trim_halo(outs[out + "_host"], h), rn.trim_halo(full, h))
+            report[out + "_bit_identical_to_1gpu"] = bool(same)
+            ok = ok and same
+    print("RESULT " + json.dumps({"rank": comm.rank, "ok": bool(ok), "report": report,
+                                  "sends": len(prog.sends), "halo": prog.halo}), flush=True)
+    prog.close()
+    comm.close()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
