@@ -311,10 +311,8 @@ def main():
 
     # end to end through the plugin call with host buffers (pinned), copies inside the timed region
     e2e = None
-    if not args.no_e2e and world == 1:
-        e2e = measure_e2e(program, prog, args, updates_per_step)
-    elif world > 1:
-        e2e = program.measure_e2e(args.steps, updates_per_step) if hasattr(program, "measure_e2e") else None
+    if not args.no_e2e:
+        e2e = measure_e2e(program, prog, args, updates_per_step, comm)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,33 +341,56 @@ def main():
         comm.close()
 
 
-def measure_e2e(program, prog, args, updates_per_step):
-    """Same metric through the reference-facing call ``program(**host_arrays)``: every step copies the
-    inputs host->device from pinned memory, runs, and copies the outputs back."""
+def measure_e2e(program, prog, args, updates_per_step, comm=None):
+    """Same metric through the reference-facing call with HOST buffers: every step copies this rank's
+    inputs host->device from pinned memory, runs the program and copies its outputs back
+    (``CudaProgram.__call__`` on one GPU; the slab-wise equivalent on several).  Wall-clock, max over ranks."""
     rtm = program.rt
-    host, keep = {}, []
+    fields = program.program.fields
+    host_in, host_out, free_host = {}, {}, []
     h2d = d2h = 0
-    free_host = []
-    for name, f in program.program.fields.items():
+    for name, f in fields.items():
         if f.is_scalar or f.kind == "intermediate":
             continue
-        if f.kind == "input" or name in program.program.outputs:
-            arr, hptr = rtm.host_alloc(f.shape, f.data_type.type)
-            free_host.append(hptr)
-            if f.kind == "input":
-                rtm.d2h(arr, program.buffers[name].dptr)     # reuse the synthetic field as host data
-                rtm.stream_synchronize()
-                h2d += arr.nbytes
-            else:
-                d2h += arr.nbytes
-            host[name + "_host"] = arr
+        shape = program.local_shape(name)
+        if f.kind == "input":
+            arr, hptr = rtm.host_alloc(shape, f.data_type.type)
+            rtm.d2h(arr, program.buffers[name].dptr)         # reuse the synthetic field as host data
+            rtm.stream_synchronize()
+            host_in[name] = arr
+            h2d += arr.nbytes
+        else:
+            arr, hptr = rtm.host_alloc(shape, f.data_type.type)
+            host_out[name] = arr
+            d2h += arr.nbytes
+        free_host.append(hptr)
     steps = max(2, min(args.steps, 5))
-    program(**host)                                           # warm
+
+    def one_step():
+        if comm is None:
+            kw = {k + "_host": v for k, v in host_in.items()}
+            kw.update({k + "_host": v for k, v in host_out.items()})
+            program(**kw)
+        else:
+            for k, v in host_in.items():
+                rtm.h2d(program.buffers[k].dptr, v)
+            program.execute()
+            for k, v in host_out.items():
+                rtm.d2h(v, program.buffers[k].dptr)
+            rtm.stream_synchronize()
+
+    one_step()                                               # warm
+    if comm is not None:
+        comm.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        program(**host)
+        one_step()
     rtm.stream_synchronize()
     dt = (time.perf_counter() - t0) / steps
+    if comm is not None:
+        dt = comm.max_float(dt)
+        h2d = int(sum(comm.allgather(h2d)))
+        d2h = int(sum(comm.allgather(d2h)))
     for hptr in free_host:
         rtm.host_free(hptr)
     return {"value": updates_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -257,10 +257,17 @@ class GroupAnalysis:
 
 
 class Geometry:
-    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch):
-        self.V, self.R, self.WR, self.WC = V, R, WR, WC
-        self.NT = 32 * WR * WC
-        self.TR, self.TC = WR * R, WC * 32 * V
+    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32):
+        """``KS`` = threads per tile row.  32 (a warp per row, k-neighbours by shuffle) in general;
+        for groups without k-taps on a narrow innermost dimension the whole extent is one row of
+        ``KS = NK / V`` threads and thread t owns row group t / KS ("flat lanes": no idle lanes)."""
+        self.V, self.R, self.WR, self.WC, self.KS = V, R, WR, WC, KS
+        self.NT = KS * WR * WC
+        if KS != 32 and (WC != 1 or self.NT % 32 or any(i.col_reach for i in ana.fields.values())):
+            raise NotStreamable("flat lanes need a single column tile and no k-taps")
+        if self.NT > 1024:
+            raise NotStreamable("too many threads")
+        self.TR, self.TC = WR * R, WC * KS * V
         h = ana.halo
         self.HJ0, self.HJ1 = h[0], h[1]
         self.HK0 = -(-h[2] // V) * V
@@ -355,8 +362,12 @@ class StreamKernelGen:
         self.fid = {name: "f{}".format(n) for n, name in enumerate(a.fields)}
 
         e("extern __shared__ __align__(1024) unsigned char sf_smem[];")
-        e("const int lane = threadIdx.x & 31;")
-        e("const int warp = threadIdx.x >> 5;")
+        if g.KS == 32:
+            e("const int lane = threadIdx.x & 31;")
+            e("const int warp = threadIdx.x >> 5;")
+        else:
+            e("const int lane = threadIdx.x % {};          // column slot within the row".format(g.KS))
+            e("const int warp = threadIdx.x / {};          // row group".format(g.KS))
         e("const int wr = warp / {};".format(g.WC))
         e("const int wc = warp % {};".format(g.WC))
         e("(void)wr; (void)wc;")
@@ -366,7 +377,7 @@ class StreamKernelGen:
         e("const int c_begin = s_begin + blockIdx.z * chunk;")
         e("const int c_end = min(c_begin + chunk, s_end);")
         e("if (c_begin >= c_end) return;")
-        e("const int c0 = (wc * 32 + lane) * {};            // first owned column inside the tile".format(V))
+        e("const int c0 = (wc * {} + lane) * {};            // first owned column inside the tile".format(g.KS, V))
         e("const int gk = tile_k0 - {} + c0;                 // its global k".format(g.HK0))
         if ndim == 3:
             e("const int r0 = wr * {};".format(R))
@@ -710,19 +721,27 @@ def choose_geometry(program, ops, options) -> Optional[Tuple[GroupAnalysis, Geom
             raise NotStreamable("innermost extent not a multiple of the vector width")
         prefetch = options.prefetch or 2
         candidates = []
+        nk = program.shape[-1]
         if ndim == 3:
             warps = options.warps or 16
             rows = [options.rows_per_thread] if options.rows_per_thread else [4, 3, 2, 1]
             for R in rows:
-                candidates.append((R, warps, 1))
+                candidates.append((R, warps, 1, 32))
+            if nk < 32 * V and nk // V <= 64:
+                # narrow innermost dimension: one row of nk/V threads, several row groups per warp
+                ks = nk // V
+                for R in rows:
+                    for groups in (options.warps * 32 // ks if options.warps else 0, 32, 24, 16):
+                        if groups and (groups * ks) % 32 == 0 and groups * ks <= 768:
+                            candidates.append((R, groups, 1, ks))
         else:
             warps = options.warps or 8
-            candidates.append((1, 1, warps))
+            candidates.append((1, 1, warps, 32))
         best = None
-        for (R, WR, WC) in candidates:
+        for (R, WR, WC, KS) in candidates:
             try:
                 ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                geo = Geometry(ana, V, R, WR, WC, prefetch)
+                geo = Geometry(ana, V, R, WR, WC, prefetch, KS)
             except NotStreamable:
                 continue
             if geo.smem > SMEM_LIMIT:
@@ -730,7 +749,8 @@ def choose_geometry(program, ops, options) -> Optional[Tuple[GroupAnalysis, Geom
             if ana.window_registers(R, V) > REG_BUDGET:
                 continue
             eff = (geo.BJ * geo.BK) / float(geo.TR * geo.TC) if ndim == 3 else geo.BK / float(geo.TC)
-            if best is None or eff > best[0]:
+            eff *= min(1.0, nk / float(geo.BK))          # lanes beyond a narrow domain are idle
+            if best is None or eff > best[0] + 1e-9:
                 best = (eff, ana, geo)
         if best is None:
             return None
@@ -763,7 +783,7 @@ def group_cost(program, ops, options):
     nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields)
     nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
     eff = _tile_efficiency(ana, geo)
-    used = min(1.0, program.shape[-1] / float(geo.BK)) if program.shape[-1] < geo.BK else 1.0
+    used = min(1.0, program.shape[-1] / float(geo.BK))
     t_mem = nbytes / HBM_BYTES_PER_S
     t_cmp = program.cells * len(ops) / (eff * used) / UPDATES_PER_S[ana.dtype.bytes]
     return max(t_mem, t_cmp) + 5e-6
@@ -787,20 +807,17 @@ def partition(program: StencilProgram, options):
     for end in range(1, n + 1):
         for start in range(max(0, end - max_depth), end):
             group = ops[start:end]
-            key = None
-            if len(group) > 1 or True:
-                # structurally identical groups (Jacobi chains) share one estimate
-                key = tuple((tuple(sorted((f, tuple(op.offsets3(f))) for f in op.accesses)) if False else
-                             (len(op.accesses), str(sorted(op.offsets3(f) for f in op.accesses)),
-                              str(op.boundary_conditions.values())))
-                            for op in group) + (len(group),)
-            cost = cache.get(key) if key in cache and _chain_like(group) else None
-            if cost is None:
+            # structurally identical chain segments (Jacobi chains) share one estimate
+            chain = _chain_like(group)
+            key = tuple((repr([op.offsets3(f) for f in op.accesses]),
+                         repr(sorted(op.boundary_conditions.items(), key=repr)[0][1:] if op.boundary_conditions else ""),
+                         op.data_type.name) for op in group) if chain else None
+            if chain and key in cache:
+                cost = cache[key]
+            else:
                 cost = group_cost(program, group, options)
-                if _chain_like(group):
-                    cache[key] = cost if cost is not None else -1.0
-            elif cost < 0:
-                cost = None
+                if chain:
+                    cache[key] = cost
             family = "streamed"
             if cost is None:
                 if len(group) > 1:
@@ -880,7 +897,8 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
     launch = LaunchSpec(kernel=name, grid_fn=grid, block=(geo.NT, 1, 1), smem=geo.smem, args=args,
                         ops=[op.name for op in ops], reads=reads, writes=stored,
                         cells_per_unit=program.cells * len(ops), family="streamed",
-                        info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "tile": [geo.TR, geo.TC],
+                        info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "threads_per_row": geo.KS,
+                              "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
                               "prefetch": geo.P, "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
