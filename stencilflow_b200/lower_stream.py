@@ -27,6 +27,7 @@ so that only program inputs and outputs touch off-chip memory (``generate_sdfg``
 import collections
 import hashlib
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 from . import dtypes
@@ -36,7 +37,7 @@ from .lower_cuda import (KernelSpec, LaunchSpec, LoweredProgram, _MATH_F32, _MAT
 from .stencil_op import JUNK_VAL, StencilOp, StencilProgram
 
 SMEM_LIMIT = 227 * 1024
-REG_BUDGET = 110          # estimated window registers per thread the planner accepts
+REG_SLACK = int(os.environ.get("SFB200_REG_SLACK", "0"))   # the estimate may exceed the per-thread limit by this much
 
 STREAM_PRELUDE = r"""
 // ---- streamed-kernel support (TMA + mbarrier, sm_100a) ----
@@ -72,6 +73,15 @@ __device__ __forceinline__ void sf_mbar_wait(void* bar, u32 parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ bool sf_elect_one() {
+    u32 pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void sf_tma_load_3d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -83,6 +93,79 @@ __device__ __forceinline__ void sf_tma_load_2d(void* dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// ---- packed float32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a) ----
+__device__ __forceinline__ float2 sf_add2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(r))
+        : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 sf_sub2(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(r))
+        : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 sf_mul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(r))
+        : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 sf_fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(r))
+        : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)),
+          "l"(reinterpret_cast<const u64&>(c)));
+    return r;
+}
+// results leave through explicit st.global (the output pointer is kept opaque to stop the compiler from
+// re-deriving it per row, which would otherwise demote these to generic stores)
+template <int N>
+__device__ __forceinline__ void sf_stg_if(bool on, float* p, const float2 (&s)[N]) {
+#pragma unroll
+    for (int q = 0; q < N; q += 2)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+                     "@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+                     ::"r"((u32)on), "l"(p + 2 * q), "f"(s[q].x), "f"(s[q].y), "f"(s[q + 1].x), "f"(s[q + 1].y) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void sf_stg_if(bool on, float* p, const float (&s)[N]) {
+#pragma unroll
+    for (int q = 0; q < N; q += 4)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+                     "@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+                     ::"r"((u32)on), "l"(p + q), "f"(s[q]), "f"(s[q + 1]), "f"(s[q + 2]), "f"(s[q + 3]) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void sf_stg_if(bool on, double* p, const double (&s)[N]) {
+#pragma unroll
+    for (int q = 0; q < N; q += 2)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+                     "@q st.global.v2.f64 [%1], {%2, %3};\n\t}"
+                     ::"r"((u32)on), "l"(p + q), "d"(s[q]), "d"(s[q + 1]) : "memory");
+}
+__device__ __forceinline__ void sf_sts_if(bool on, float* p, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.f32 [%1], %2;\n\t}"
+                 ::"r"((u32)on), "r"(sf_smem_addr(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sf_sts_if(bool on, double* p, double v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.f64 [%1], %2;\n\t}"
+                 ::"r"((u32)on), "r"(sf_smem_addr(p)), "d"(v) : "memory");
+}
+template <int V>
+__device__ __forceinline__ void sf_ldp(float2* dst, const float* __restrict__ p) {
+    SfVec<float, V> t = *reinterpret_cast<const SfVec<float, V>*>(p);
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) dst[q] = make_float2(t.v[2 * q], t.v[2 * q + 1]);
+}
+template <int V>
+__device__ __forceinline__ void sf_stp(float* __restrict__ p, const float2* src) {
+    SfVec<float, V> t;
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) { t.v[2 * q] = src[q].x; t.v[2 * q + 1] = src[q].y; }
+    *reinterpret_cast<SfVec<float, V>*>(p) = t;
 }
 """
 
@@ -255,6 +338,16 @@ class GroupAnalysis:
         per = self.dtype.bytes // 4
         return sum(i.window for i in self.fields.values() if i.consumed) * R * V * per
 
+    def register_estimate(self, R, V):
+        """Registers per thread the generated kernel needs: the planes of every window that are
+        live across steps (the oldest plane of a window dies while the newest is being produced)
+        plus what is in flight -- the plane being produced, its consumer's result, the pre-fetched
+        neighbour cells of the next operator, addresses, masks and loop state.  The constant part is
+        fitted to ptxas' allocations of the Jacobi/hdiff kernels (spill-free iff estimate <= limit)."""
+        per = self.dtype.bytes // 4
+        live = sum(max(1, i.window - 1) for i in self.fields.values() if i.consumed)
+        return (live + 2) * R * V * per + 8 + min(12, R * V * per) * len(self.ops)
+
 
 class Geometry:
     def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32):
@@ -305,7 +398,7 @@ class Geometry:
                 off = (off + 127) & ~127
             if i.col_ring:
                 self.xcol_off[i.name] = off
-                off += i.col_ring * self.WR * self.WC * 2 * self.R * self.V * b
+                off += i.col_ring * self.WR * self.WC * 2 * self.R * i.col_reach * b
                 off = (off + 127) & ~127
         self.bar_off = off
         off += 8 * self.D
@@ -317,8 +410,22 @@ def _fmt_off(x):
 
 
 class StreamKernelGen:
+    """Emits the CUDA C++ of one fused pass.
+
+    Two code-shape decisions matter for the instruction count (the pass is issue-bound once it is
+    fused):
+
+    * the streamed loop is unrolled ``U`` times, ``U`` a common multiple of the periods of the rotating
+      resources (register windows, TMA ring, exchange rings), so that every window slot and ring slot
+      is a compile-time constant: no register-to-register window rotation, no modulo arithmetic;
+    * float32 groups compute on *pairs* of neighbouring cells with Blackwell's packed
+      ``add/mul/fma.rn.f32x2`` (SASS ``FADD2/FMUL2/FFMA2``): one issue slot per two cells.  Taps whose
+      two cells do not sit in one aligned register pair (odd k-offsets, cells from another lane) fall
+      back to two scalar operations, which still write an aligned pair.
+    """
+
     def __init__(self, program: StencilProgram, ops: List[StencilOp], ana: GroupAnalysis, geo: Geometry,
-                 specialize=None):
+                 specialize=None, max_unroll=None, pack=None):
         self.program, self.ops, self.ana, self.geo = program, ops, ana, geo
         self.specialize = specialize or {}
         self.ct = ana.dtype
@@ -331,6 +438,63 @@ class StreamKernelGen:
                 if s not in program.constants and s not in self.specialize and s not in self.scalars:
                     self.scalars.append(s)
         self.lines: List[str] = []
+        if pack is None:
+            pack = os.environ.get("SFB200_PACK", "1") != "0"
+        if max_unroll is None:
+            max_unroll = int(os.environ.get("SFB200_UNROLL", "6"))
+        self.G = 2 if (pack and self.ct == dtypes.float32 and geo.V % 2 == 0) else 1
+        self.VH = geo.V // self.G
+        self.ET = "float2" if self.G == 2 else self.T
+        self.U = self._choose_unroll(max(1, max_unroll))
+        self.pipeline = os.environ.get("SFB200_PIPELINE", "1") != "0"
+        self.fast_path = os.environ.get("SFB200_FASTPATH", "1") != "0"
+        self.with_bc = True
+        self._tmp = 0
+
+    # ------------------------------------------------------------------ unrolling
+    def _choose_unroll(self, cap):
+        a, g = self.ana, self.geo
+        windows = [i.window for i in a.fields.values() if i.consumed and i.window > 1]
+        rings = [i.row_ring for i in a.fields.values() if i.row_ring]
+        rings += [i.col_ring for i in a.fields.values() if i.col_ring]
+        wmax = max(windows + [1])
+        for periods in ([g.D] + rings, [g.D], []):
+            base = 1
+            for n in periods:
+                base = base * n // math.gcd(base, n)
+            u = base * -(-wmax // base)          # smallest multiple of the smem periods covering every window
+            if u <= cap:
+                return u
+        return 1
+
+    def static(self, period):
+        return self.U % period == 0
+
+    def wperiod(self, info):
+        """Renaming period of a register window.  Slots that hold no live plane cost no register, so
+        a window is padded to the unroll factor whenever that is large enough; only a window longer
+        than the unroll factor falls back to rotation by moves (period 0)."""
+        if info.window == 1:
+            return 1
+        if self.U >= info.window:
+            return self.U
+        return info.window if self.U % info.window == 0 else 0
+
+    def wslot(self, info, age, u):
+        """window slot holding the plane of ``age`` once the field has been produced at position u"""
+        n = self.wperiod(info)
+        if n == 1:
+            return 0
+        if n:
+            return (u - age) % n
+        return age
+
+    def ring_slot(self, var, n, age, u):
+        if self.static(n):
+            return str((u - age) % n)
+        if age == 0:
+            return var
+        return "(({rv} + {k}) % {n})".format(rv=var, k=n - (age % n), n=n)
 
     # ------------------------------------------------------------------ small emit helpers
     def emit(self, text, indent=1):
@@ -339,11 +503,24 @@ class StreamKernelGen:
     def lit(self, v):
         return literal(v, self.ct)
 
-    def _slot_expr(self, ring_var, ring, age):
-        """index of the ring slot written ``age`` steps ago (ring_var = slot written this step)."""
-        if age == 0:
-            return ring_var
-        return "(({rv} + {k}) % {n})".format(rv=ring_var, k=ring - (age % ring), n=ring)
+    def tmp(self):
+        self._tmp += 1
+        return "q{}".format(self._tmp)
+
+    def cellref(self, vec, c):
+        if self.G == 2:
+            return "{}[{}].{}".format(vec, c // 2, "xy"[c % 2])
+        return "{}[{}]".format(vec, c)
+
+    def ldv(self, dst, src):
+        if self.G == 2:
+            return "sf_ldp<{}>({}, {});".format(self.geo.V, dst, src)
+        return "sf_ldv<{}, {}>({}, {});".format(self.T, self.geo.V, dst, src)
+
+    def stv(self, dst, src):
+        if self.G == 2:
+            return "sf_stp<{}>({}, {});".format(self.geo.V, dst, src)
+        return "sf_stv<{}, {}>({}, {});".format(self.T, self.geo.V, dst, src)
 
     # ------------------------------------------------------------------ kernel text
     def generate(self):
@@ -352,6 +529,7 @@ class StreamKernelGen:
         e = self.emit
         ndim = a.ndim
         ext = a.ext_fields
+        U = self.U
         stored = [i for i in a.fields.values() if i.stored]
         params = ["const __grid_constant__ CUtensorMap tm_{}".format(n) for n in range(len(ext))]
         params += ["{}* __restrict__ o_{}".format(T, n) for n in range(len(stored))]
@@ -399,6 +577,14 @@ class StreamKernelGen:
         e("}")
         full_mask = (1 << (R * V)) - 1
         e("const bool interior = __syncthreads_and(cmask == {}u);".format(full_mask))
+        if ndim == 3:
+            e("i64 out_off = ((i64)gj0 - (i64)s_base * {NJ}) * {NK} + gk;   // element offset of the thread's first cell in plane 0".format(NJ=self.NJ, NK=self.NK))
+        else:
+            e("i64 out_off = (i64)gk - (i64)s_base * {NK};".format(NK=self.NK))
+        e("asm volatile(\"\" : \"+r\"(cmask), \"+r\"(smask));   // keep them in registers: no re-derivation from blockIdx in the loop")
+        for n in range(len(stored)):
+            e("{T}* ob_{n} = o_{n} + out_off;".format(T=T, n=n))
+            e("asm volatile(\"\" : \"+l\"(ob_{n}));".format(n=n))
         # shared memory carve-up
         for n, i in enumerate(ext):
             e("{T}* const tile_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
@@ -417,55 +603,88 @@ class StreamKernelGen:
         e("}")
         e("__syncthreads();")
         # register windows
+        zero = "make_float2(0.0f, 0.0f)" if self.G == 2 else self.lit(0)
         for i in a.fields.values():
             if i.consumed:
-                e("{T} w_{f}[{W}][{R}][{V}];".format(T=T, f=self.fid[i.name], W=i.window, R=R, V=V))
+                W = self.wperiod(i) or i.window
+                e("{ET} w_{f}[{W}][{R}][{VH}];".format(ET=self.ET, f=self.fid[i.name], W=W, R=R, VH=self.VH))
                 e("#pragma unroll")
-                e("for (int a = 0; a < {}; ++a)".format(i.window))
+                e("for (int a = 0; a < {}; ++a)".format(W))
                 e("#pragma unroll", 2)
                 e("for (int r = 0; r < {}; ++r)".format(R), 2)
                 e("#pragma unroll", 3)
-                e("for (int v = 0; v < {}; ++v) w_{}[a][r][v] = {};".format(V, self.fid[i.name], self.lit(0)), 3)
-            if i.row_ring:
+                e("for (int v = 0; v < {}; ++v) w_{}[a][r][v] = {};".format(self.VH, self.fid[i.name], zero), 3)
+            if i.row_ring and not self.static(i.row_ring):
                 e("int xr_{} = 0;".format(self.fid[i.name]))
-            if i.col_ring:
+            if i.col_ring and not self.static(i.col_ring):
                 e("int xc_{} = 0;".format(self.fid[i.name]))
         tile_bytes = g.TR * g.TC * self.ct.bytes
-        e("const int t_begin = c_begin + ({});".format(a.t_begin_offset()))
         e("const int t_end = c_end + ({});".format(a.t_end_offset()))
-        e("int slot = 0; u32 phase = 0;")
+        if U > 1:
+            # the step count is rounded up to a multiple of the unroll factor by starting earlier:
+            # the extra leading steps only produce planes nobody stores or reads
+            e("const int t_begin = t_end - ((t_end - (c_begin + ({off})) + {Um1}) / {U}) * {U};".format(
+                off=a.t_begin_offset(), Um1=U - 1, U=U))
+        else:
+            e("const int t_begin = c_begin + ({});".format(a.t_begin_offset()))
+        static_d = self.static(g.D)
+        if static_d:
+            e("u32 phase = 0;")
+        else:
+            e("int slot = 0; u32 phase = 0;")
         # TMA issue helper as a lambda
-        e("auto issue = [&](int t, int s) {")
-        e("sf_mbar_expect_tx(&bars[s], {});".format(tile_bytes * len(ext)), 2)
         nbox = g.TC // g.box_cols
+        nwarps = g.NT // 32
+        total_boxes = nbox * len(ext)
+        # one elected lane of warp 0 arms the mbarrier; with many boxes per plane (wide 2-D tiles) the
+        # copies themselves are issued by the first `issuers` warps, one box each per round
+        issuers = 1 if total_boxes <= 2 else min(nwarps, nbox)
+        e("const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform")
+        e("auto issue = [&](int t, int s) {")
+        e("if (warp_u == 0) sf_mbar_expect_tx(&bars[s], {});".format(tile_bytes * len(ext)), 2)
         for n, i in enumerate(ext):
             plane = "t - ({}) - s_base".format(i.lag)
-            for b in range(nbox):
-                dst = "tile_{f} + s * {sz} + {bo}".format(f=self.fid[i.name], sz=g.TR * g.TC, bo=b * g.box_cols)
+            if issuers == 1:
+                boxes = [str(b * g.box_cols) for b in range(nbox)]
+            else:
+                e("for (int b = warp_u; b < {}; b += {}) {{".format(nbox, issuers), 2)
+                boxes = ["b * {}".format(g.box_cols)]
+            for bo in boxes:
+                dst = "tile_{f} + s * {sz} + {bo}".format(f=self.fid[i.name], sz=g.TR * g.TC, bo=bo)
                 if ndim == 3:
                     e("sf_tma_load_3d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, tile_j0 - {}, {});".format(
-                        dst, n, g.HK0, b * g.box_cols, g.HJ0, plane), 2)
+                        dst, n, g.HK0, bo, g.HJ0, plane), 2)
                 else:
                     e("sf_tma_load_2d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, {});".format(
-                        dst, n, g.HK0, b * g.box_cols, plane), 2)
+                        dst, n, g.HK0, bo, plane), 2)
+            if issuers > 1:
+                e("}", 2)
         e("};")
-        e("if (threadIdx.x == 0) {")
+        e("const bool issuer = warp_u < {};".format(issuers))
+        e("if (issuer && sf_elect_one()) {")
         e("for (int p = 0; p < {}; ++p) if (t_begin + p < t_end) issue(t_begin + p, p);".format(g.P), 2)
         e("}")
-        e("for (int t = t_begin; t < t_end; ++t) {")
-        e("if (threadIdx.x == 0 && t + {P} < t_end) issue(t + {P}, (slot + {P}) % {D});".format(P=g.P, D=g.D), 2)
-        e("sf_mbar_wait(&bars[slot], phase);", 2)
-        for i in ext:
-            self._produce_ext(i)
-        for op in self.ops:
-            self._produce_op(op)
-        e("__syncthreads();", 2)
-        e("if (++slot == {}) {{ slot = 0; phase ^= 1; }}".format(g.D), 2)
-        for i in a.fields.values():
-            if i.row_ring:
-                e("if (++xr_{f} == {n}) xr_{f} = 0;".format(f=self.fid[i.name], n=i.row_ring), 2)
-            if i.col_ring:
-                e("if (++xc_{f} == {n}) xc_{f} = 0;".format(f=self.fid[i.name], n=i.col_ring), 2)
+        e("#pragma unroll 1")
+        e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
+        needs_bc = [i for i in a.fields.values() if self._needs_fixup(i)]
+        variants = [True]
+        if needs_bc and self.fast_path:
+            # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no
+            # boundary values: it runs a copy of the steps without any of that code
+            lag_max = max(i.lag for i in needs_bc)
+            lag_min = min(i.lag for i in needs_bc)
+            e("const bool fast = __all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}));".format(
+                lag_max, U - 1, lag_min, self.NS), 2)
+            variants = [False, True]
+        for with_bc in variants:
+            self.with_bc = with_bc
+            if len(variants) == 2:
+                e("if (fast) {" if not with_bc else "} else {", 2)
+            self._emit_steps(ext, static_d)
+        if len(variants) == 2:
+            e("}", 2)
+        if static_d and (U // g.D) % 2 == 1:
+            e("phase ^= 1u;", 2)
         e("}")
         body = "\n".join(self.lines)
         digest = hashlib.sha1((body + ";".join(params)).encode()).hexdigest()[:12]
@@ -478,6 +697,52 @@ class StreamKernelGen:
         args += [("slab",), ("chunk",)]
         return name, src, args
 
+    def _needs_fixup(self, info):
+        """Cells outside the domain must read as the boundary value.  Input planes arrive through TMA,
+        which zero-fills everything outside the tensor, so a zero boundary value needs no code."""
+        if not info.consumed or info.bc is None:
+            return False
+        return not (info.kind == "ext" and float(info.bc) == 0.0)
+
+    def _emit_steps(self, ext, static_d):
+        g, a, e, U = self.geo, self.ana, self.emit, self.U
+        for u in range(U):
+            e("{{  // ---- unrolled step {}".format(u), 2)
+            e("const int t = t0 + {};".format(u), 2)
+            if static_d:
+                self.slot_expr = str(u % g.D)
+                nxt = str((u + g.P) % g.D)
+                ph = "phase" if (u // g.D) % 2 == 0 else "(phase ^ 1u)"
+            else:
+                self.slot_expr = "slot"
+                nxt = "(slot + {P}) % {D}".format(P=g.P, D=g.D)
+                ph = "phase"
+            e("if (issuer && t + {P} < t_end) {{ if (sf_elect_one()) issue(t + {P}, {nxt}); }}".format(P=g.P, nxt=nxt), 2)
+            gathered = {}
+            if self.pipeline and self._can_gather_early(self.ops[0]):
+                # neighbour data of the first operator is a step old: fetch it while the TMA lands
+                gathered[0] = self._gather_op(self.ops[0], u, 0)
+            e("sf_mbar_wait(&bars[{}], {});".format(self.slot_expr, ph), 2)
+            for i in ext:
+                self._produce_ext(i, u)
+            for k, op in enumerate(self.ops):
+                if k not in gathered:
+                    gathered[k] = self._gather_op(op, u, k)
+                if self.pipeline and k + 1 < len(self.ops) and self._can_gather_early(self.ops[k + 1]):
+                    # software pipelining: the shuffles / ring loads of the next operator are issued
+                    # before this operator's arithmetic, which hides their latency
+                    gathered[k + 1] = self._gather_op(self.ops[k + 1], u, k + 1)
+                self._produce_op(op, u, gathered.pop(k))
+            e("__syncthreads();", 2)
+            if not static_d:
+                e("if (++slot == {}) {{ slot = 0; phase ^= 1; }}".format(g.D), 2)
+            for i in a.fields.values():
+                if i.row_ring and not self.static(i.row_ring):
+                    e("if (++xr_{f} == {n}) xr_{f} = 0;".format(f=self.fid[i.name], n=i.row_ring), 2)
+                if i.col_ring and not self.static(i.col_ring):
+                    e("if (++xc_{f} == {n}) xc_{f} = 0;".format(f=self.fid[i.name], n=i.col_ring), 2)
+            e("}", 2)
+
     def _box(self):
         g = self.geo
         if self.ana.ndim == 3:
@@ -485,76 +750,101 @@ class StreamKernelGen:
         return [g.box_cols, 1]
 
     # ------------------------------------------------------------------ producing a field
-    def _finish_field(self, info: _FieldInfo, plane_expr: str):
-        """``nv`` holds the new plane: apply the boundary value, rotate the window, publish edges."""
+    def _open_plane(self, info: _FieldInfo, u: int):
+        """Declares ``nv``, the R x V cells of the plane being produced: the window slot that becomes
+        age 0 (rotating the window by moves only when its period does not divide the unroll factor)."""
+        g, e = self.geo, self.emit
+        f = self.fid[info.name]
+        if not info.consumed:
+            e("{ET} nv[{R}][{VH}];".format(ET=self.ET, R=g.R, VH=self.VH), 3)
+            return
+        if self.wperiod(info) == 0:
+            for wdx in range(info.window - 1, 0, -1):
+                e("#pragma unroll", 3)
+                e("for (int r = 0; r < {}; ++r)".format(g.R), 3)
+                e("#pragma unroll", 4)
+                e("for (int v = 0; v < {VH}; ++v) w_{f}[{a}][r][v] = w_{f}[{b}][r][v];".format(
+                    VH=self.VH, f=f, a=wdx, b=wdx - 1), 4)
+        e("{ET} (&nv)[{R}][{VH}] = w_{f}[{s}];".format(ET=self.ET, R=g.R, VH=self.VH, f=f,
+                                                      s=self.wslot(info, 0, u)), 3)
+
+    def _finish_field(self, info: _FieldInfo, plane_expr: str, u: int):
+        """``nv`` holds the new plane: apply the boundary value, publish the edge rows/columns."""
         g, e = self.geo, self.emit
         f = self.fid[info.name]
         V, R = g.V, g.R
-        if info.consumed and info.bc is not None:
+        if not info.consumed:
+            return
+        if self.with_bc and self._needs_fixup(info):
             e("{")
             e("const bool pin = (unsigned)({}) < {}u;".format(plane_expr, self.NS), 3)
             e("if (!(pin && interior)) {", 3)
             e("const u32 m = pin ? cmask : 0u;", 4)
-            e("#pragma unroll", 4)
-            e("for (int r = 0; r < {}; ++r)".format(R), 4)
-            e("#pragma unroll", 5)
-            e("for (int v = 0; v < {V}; ++v) if (!((m >> (r * {V} + v)) & 1u)) nv[r][v] = {bc};".format(
-                V=V, bc=self.lit(info.bc)), 5)
+            for r in range(R):
+                for v in range(V):
+                    e("if (!((m >> {b}) & 1u)) {c} = {bc};".format(
+                        b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=self.lit(info.bc)), 4)
             e("}", 3)
             e("}")
-        if not info.consumed:
-            return
-        for wdx in range(info.window - 1, 0, -1):
-            e("#pragma unroll", 2)
-            e("for (int r = 0; r < {}; ++r)".format(R), 2)
-            e("#pragma unroll", 3)
-            e("for (int v = 0; v < {V}; ++v) w_{f}[{a}][r][v] = w_{f}[{b}][r][v];".format(
-                V=V, f=f, a=wdx, b=wdx - 1), 3)
-        e("#pragma unroll", 2)
-        e("for (int r = 0; r < {}; ++r)".format(R), 2)
-        e("#pragma unroll", 3)
-        e("for (int v = 0; v < {V}; ++v) w_{f}[0][r][v] = nv[r][v];".format(V=V, f=f), 3)
         if info.row_ring:
             n = info.row_reach
             # layout [ring][WR][2][n][TC]
-            base = "xrow_{f} + ((xr_{f} * {WR} + wr) * 2) * {sz}".format(f=f, WR=g.WR, sz=n * g.TC)
+            slot = self.ring_slot("xr_" + f, info.row_ring, 0, u)
+            base = "xrow_{f} + (({slot} * {WR} + wr) * 2) * {sz}".format(f=f, slot=slot, WR=g.WR, sz=n * g.TC)
             for q in range(n):
-                e("sf_stv<{T}, {V}>({base} + {o} + c0, nv[{r}]);".format(
-                    T=self.T, V=V, base=base, o=q * g.TC, r=q), 2)
-                e("sf_stv<{T}, {V}>({base} + {o} + c0, nv[{r}]);".format(
-                    T=self.T, V=V, base=base, o=(n + q) * g.TC, r=R - n + q), 2)
+                e(self.stv("{base} + {o} + c0".format(base=base, o=q * g.TC), "nv[{}]".format(q)), 2)
+                e(self.stv("{base} + {o} + c0".format(base=base, o=(n + q) * g.TC), "nv[{}]".format(R - n + q)), 2)
         if info.col_ring:
-            # layout [ring][WR][WC][2][R][V]
-            base = "xcol_{f} + (((xc_{f} * {WR} + wr) * {WC} + wc) * 2) * {sz}".format(
-                f=f, WR=g.WR, WC=g.WC, sz=R * V)
-            e("if (lane == 0) {", 2)
+            # layout [ring][WR][WC][2][R][n]: the n = col_reach edge cells of every owned row, left
+            # edge (side 0, written by lane 0) and right edge (side 1, written by lane 31)
+            n = info.col_reach
+            slot = self.ring_slot("xc_" + f, info.col_ring, 0, u)
+            base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + wc) * 2) * {sz}".format(
+                f=f, slot=slot, WR=g.WR, WC=g.WC, sz=R * n)
             for r in range(R):
-                e("sf_stv<{T}, {V}>({base} + {o}, nv[{r}]);".format(T=self.T, V=V, base=base, o=r * V, r=r), 3)
-            e("}", 2)
-            e("if (lane == 31) {", 2)
+                for q in range(n):
+                    e("sf_sts_if(lane == 0, {base} + {o}, {c});".format(
+                        base=base, o=r * n + q, c=self.cellref("nv[{}]".format(r), q)), 2)
             for r in range(R):
-                e("sf_stv<{T}, {V}>({base} + {o}, nv[{r}]);".format(T=self.T, V=V, base=base, o=(R + r) * V, r=r), 3)
-            e("}", 2)
+                for q in range(n):
+                    e("sf_sts_if(lane == 31, {base} + {o}, {c});".format(
+                        base=base, o=(R + r) * n + q, c=self.cellref("nv[{}]".format(r), V - n + q)), 2)
 
-    def _produce_ext(self, info: _FieldInfo):
+    def _produce_ext(self, info: _FieldInfo, u: int):
         g, e = self.geo, self.emit
         f = self.fid[info.name]
         e("{  // input field " + f, 2)
-        e("{T} nv[{R}][{V}];".format(T=self.T, R=g.R, V=g.V), 3)
+        self._open_plane(info, u)
         for r in range(g.R):
             row = "(r0 + {})".format(r) if self.ana.ndim == 3 else "0"
-            e("sf_ldv<{T}, {V}>(nv[{r}], tile_{f} + slot * {sz} + {row} * {TC} + c0);".format(
-                T=self.T, V=g.V, r=r, f=f, sz=g.TR * g.TC, row=row, TC=g.TC), 3)
-        self._finish_field(info, "t - ({})".format(info.lag))
+            e(self.ldv("nv[{}]".format(r), "tile_{f} + {slot} * {sz} + {row} * {TC} + c0".format(
+                f=f, slot=self.slot_expr, sz=g.TR * g.TC, row=row, TC=g.TC)), 3)
+        self._finish_field(info, "t - ({})".format(info.lag), u)
         e("}", 2)
 
-    def _produce_op(self, op: StencilOp):
+    def _can_gather_early(self, op: StencilOp):
+        """True when the operator's neighbour data (shuffled cells, ring rows) can be fetched before
+        its sources are produced in the current step: exchange taps are at least one step old by
+        construction, so only move-rotated windows (whose slots shift at production) forbid it."""
+        a = self.ana
+        info = a.fields[op.name]
+        for (field, d, dj, dk) in a.taps[op.name]:
+            src = a.fields[field]
+            if dj == 0 and dk == 0:
+                continue
+            if info.lag - d - src.lag < 1:
+                return False        # shuffles of the plane produced in this very step
+            if self.wperiod(src) == 0:
+                return False
+        return True
+
+    def _gather_op(self, op: StencilOp, u: int, k: int):
+        """Emits the loads of everything operator ``op`` reads from other threads (warp shuffles for
+        k-neighbours, exchange-ring rows for j-neighbours) and returns the naming tables."""
         g, a, e = self.geo, self.ana, self.emit
         info = a.fields[op.name]
         V, R, T = g.V, g.R, self.T
         taps = a.taps[op.name]
-        plane = "t - ({})".format(info.lag)
-        e("{  // operator producing " + self.fid[op.name], 2)
         # row vectors needed: (field, age, row) ; shifts needed per row vector
         rows = collections.OrderedDict()
         for (field, d, dj, dk) in taps:
@@ -571,16 +861,16 @@ class StreamKernelGen:
         for (field, age, rr), (nl, nr) in rows.items():
             src = a.fields[field]
             f = self.fid[field]
-            tag = "{}_{}_{}".format(f, age, _fmt_off(rr))
+            tag = "o{}_{}_{}_{}".format(k, f, age, _fmt_off(rr))
             if 0 <= rr < R:
-                vec = "w_{}[{}][{}]".format(f, age, rr)
-                names[(field, age, rr)] = (vec, tag, "own")
+                vec = "w_{}[{}][{}]".format(f, self.wslot(src, age, u), rr)
+                names[(field, age, rr)] = (vec, tag)
                 if nl or nr:
-                    self._emit_shifts(src, vec, tag, rr, age, nl, nr)
+                    self._emit_shifts(src, vec, tag, rr, age, nl, nr, u)
             else:
                 # a row owned by the neighbouring warp: read it (and its shifted columns) from the ring
                 n = src.row_reach
-                slot = self._slot_expr("xr_" + f, src.row_ring, age)
+                slot = self.ring_slot("xr_" + f, src.row_ring, age, u)
                 if rr < 0:
                     nbr = "max(wr - 1, 0)"
                     side_row = n + (n + rr)          # bottom rows of the warp above
@@ -590,9 +880,9 @@ class StreamKernelGen:
                 base = "xrow_{f} + (({slot} * {WR} + {nbr}) * 2) * {sz} + {o}".format(
                     f=f, slot=slot, WR=g.WR, nbr=nbr, sz=n * g.TC, o=side_row * g.TC)
                 e("const {T}* const p_{tag} = {base};".format(T=T, tag=tag, base=base), 3)
-                e("{T} x_{tag}[{V}];".format(T=T, tag=tag, V=V), 3)
-                e("sf_ldv<{T}, {V}>(x_{tag}, p_{tag} + c0);".format(T=T, V=V, tag=tag), 3)
-                names[(field, age, rr)] = ("x_" + tag, tag, "ring")
+                e("{ET} x_{tag}[{VH}];".format(ET=self.ET, tag=tag, VH=self.VH), 3)
+                e(self.ldv("x_" + tag, "p_{} + c0".format(tag)), 3)
+                names[(field, age, rr)] = ("x_" + tag, tag)
                 if nl:
                     e("{T} l_{tag}[{n}];".format(T=T, tag=tag, n=nl), 3)
                     for q in range(nl):
@@ -602,33 +892,64 @@ class StreamKernelGen:
                     for q in range(nr):
                         e("g_{tag}[{q}] = p_{tag}[min(c0 + {V} + {q}, {last})];".format(
                             tag=tag, q=q, V=V, last=g.TC - 1), 3)
+        return rows, names
 
-        def tap_c(t: ex.Tap, r: int, v: int) -> str:
+    def _produce_op(self, op: StencilOp, u: int, gathered):
+        g, a, e = self.geo, self.ana, self.emit
+        info = a.fields[op.name]
+        V, R, T = g.V, g.R, self.T
+        plane = "t - ({})".format(info.lag)
+        rows, names = gathered
+        e("{  // operator producing " + self.fid[op.name], 2)
+
+        def tap_key(t: ex.Tap, r: int):
             if a.ndim == 3:
                 d, dj, dk = t.offset
             else:
                 d, dj, dk = t.offset[1], 0, t.offset[2]
             src = a.fields[t.field]
             age = info.lag - d - src.lag
-            vec, tag, kind = names[(t.field, age, r + dj)]
-            c = v + dk
-            nl, nr = rows[(t.field, age, r + dj)]
+            return (t.field, age, r + dj), dk
+
+        def tap_cell(t: ex.Tap, r: int, c: int) -> str:
+            """C expression of the cell at column c (relative to the thread's first cell)"""
+            key, _ = tap_key(t, r)
+            vec, tag = names[key]
+            nl, nr = rows[key]
             if 0 <= c < V:
-                return "{}[{}]".format(vec, c)
+                return self.cellref(vec, c)
             if c < 0:
                 return "l_{}[{}]".format(tag, nl + c)
             return "g_{}[{}]".format(tag, c - V)
 
+        self._open_plane(info, u)
+        if self.G == 1:
+            self._emit_scalar_cells(op, tap_key, tap_cell)
+        else:
+            self._emit_packed_cells(op, names, tap_key, tap_cell)
+        if info.stored:
+            idx = [i.name for i in a.fields.values() if i.stored].index(op.name)
+            e("{T}* op = ob_{n} + (i64)({p}) * {stride};".format(
+                T=T, n=idx, p=plane, stride=(self.NJ * self.NK if a.ndim == 3 else self.NK)), 3)
+            e("asm volatile(\"\" : \"+l\"(op));              // one address computation for all rows", 3)
+            e("const bool inchunk = ({p}) >= c_begin && ({p}) < c_end;".format(p=plane), 3)
+            for r in range(R):
+                e("sf_stg_if(inchunk && (smask & {m}u), op + {o}, nv[{r}]);".format(m=1 << r, o=r * self.NK, r=r), 3)
+        self._finish_field(info, plane, u)
+        e("}", 2)
+
+    # ------------------------------------------------------------------ expressions, one cell at a time
+    def _emit_scalar_cells(self, op, tap_key, tap_cell):
+        g, e, T = self.geo, self.emit, self.T
         math_fn = _MATH_F32 if self.ct == dtypes.float32 else _MATH_F64
-        e("{T} nv[{R}][{V}];".format(T=T, R=R, V=V), 3)
         local_ids = {}
-        for r in range(R):
-            for v in range(V):
+        for r in range(g.R):
+            for v in range(g.V):
                 local = {}
                 for s in op.statements:
                     rhs = ex.emit_c(
                         s.value,
-                        tap=lambda t, r=r, v=v: tap_c(t, r, v),
+                        tap=lambda t, r=r, v=v: tap_cell(t, r, v + tap_key(t, r)[1]),
                         var=lambda n, local=local: self._var(n, local, op),
                         literal=self.lit,
                         call=lambda fn, args: "{}({})".format(math_fn[fn], ", ".join(args)))
@@ -641,24 +962,172 @@ class StreamKernelGen:
                     e("{} {} = {};".format(ty, lname, rhs), 3)
                     local[s.target] = lname
                 target = op.name if op.name in local else op.statements[-1].target
-                e("nv[{}][{}] = {};".format(r, v, local[target]), 3)
-        if info.stored:
-            idx = [i.name for i in a.fields.values() if i.stored].index(op.name)
-            e("if (({p}) >= c_begin && ({p}) < c_end) {{".format(p=plane), 3)
-            if a.ndim == 3:
-                e("{T}* const op = o_{n} + ((i64)(({p}) - s_base) * {NJ} + gj0) * {NK} + gk;".format(
-                    T=T, n=idx, p=plane, NJ=self.NJ, NK=self.NK), 4)
-            else:
-                e("{T}* const op = o_{n} + (i64)(({p}) - s_base) * {NK} + gk;".format(
-                    T=T, n=idx, p=plane, NK=self.NK), 4)
-            for r in range(R):
-                e("if (smask & {m}u) sf_stv<{T}, {V}>(op + {o}, nv[{r}]);".format(
-                    m=1 << r, T=T, V=V, o=r * self.NK, r=r), 4)
-            e("}", 3)
-        self._finish_field(info, plane)
-        e("}", 2)
+                e("{} = {};".format(self.cellref("nv[{}]".format(r), v), local[target]), 3)
 
-    def _emit_shifts(self, src, vec, tag, rr, age, nl, nr):
+    # ------------------------------------------------------------------ expressions, two cells at a time
+    def _emit_packed_cells(self, op, names, tap_key, tap_cell):
+        """float32: every value is a pair of neighbouring cells (2h, 2h+1) of one row.
+
+        Value kinds: ("p", float2 lvalue) | ("s", lo, hi) scalar float expressions that do not form an
+        aligned register pair | ("c", uniform scalar expression) | ("b", lo, hi) boolean lanes |
+        ("cb", uniform boolean)."""
+        g, e, V = self.geo, self.emit, self.geo.V
+        math_fn = _MATH_F32
+
+        for r in range(g.R):
+            for h in range(V // 2):
+                local = {}
+
+                def lanes(v):
+                    if v[0] == "p":
+                        return v[1] + ".x", v[1] + ".y"
+                    if v[0] in ("c", "cb"):
+                        return v[1], v[1]
+                    return v[1], v[2]
+
+                def as_pair(v):
+                    if v[0] == "p":
+                        return v[1]
+                    assert v[0] == "c"
+                    return "make_float2({0}, {0})".format(v[1])
+
+                def new_pair(lo, hi):
+                    n = self.tmp()
+                    e("float2 {n}; {n}.x = {lo}; {n}.y = {hi};".format(n=n, lo=lo, hi=hi), 3)
+                    return ("p", n)
+
+                def packed(fn, *vals):
+                    n = self.tmp()
+                    e("const float2 {n} = {fn}({args});".format(n=n, fn=fn, args=", ".join(as_pair(v) for v in vals)), 3)
+                    return ("p", n)
+
+                def packable(*vals):
+                    return all(v[0] in ("p", "c") for v in vals) and any(v[0] == "p" for v in vals)
+
+                def negc(v):
+                    return ("c", "(-{})".format(v[1]))
+
+                def val(x):
+                    if isinstance(x, ex.Const):
+                        if isinstance(x.value, bool):
+                            return ("cb", "true" if x.value else "false")
+                        return ("c", self.lit(x.value))
+                    if isinstance(x, ex.Var):
+                        if x.name in local:
+                            return local[x.name]
+                        return ("c", self._var(x.name, {}, op))
+                    if isinstance(x, ex.Tap):
+                        key, dk = tap_key(x, r)
+                        vec, tag = names[key]
+                        c = 2 * h + dk
+                        if dk % 2 == 0 and 0 <= c and c + 1 < V:
+                            return ("p", "{}[{}]".format(vec, c // 2))
+                        return ("s", tap_cell(x, r, c), tap_cell(x, r, c + 1))
+                    if isinstance(x, ex.Bin):
+                        if x.op in "+-":
+                            fused = fma(x)
+                            if fused is not None:
+                                return fused
+                        va, vb = val(x.a), val(x.b)
+                        if va[0] == "c" and vb[0] == "c":
+                            return ("c", "({} {} {})".format(va[1], x.op, vb[1]))
+                        if x.op in "+-*" and packable(va, vb):
+                            return packed({"+": "sf_add2", "-": "sf_sub2", "*": "sf_mul2"}[x.op], va, vb)
+                        (alo, ahi), (blo, bhi) = lanes(va), lanes(vb)
+                        return new_pair("({} {} {})".format(alo, x.op, blo), "({} {} {})".format(ahi, x.op, bhi))
+                    if isinstance(x, ex.Neg):
+                        va = val(x.a)
+                        if va[0] == "c":
+                            return negc(va)
+                        lo, hi = lanes(va)
+                        return new_pair("(-{})".format(lo), "(-{})".format(hi))
+                    if isinstance(x, ex.Cmp):
+                        va, vb = val(x.a), val(x.b)
+                        if va[0] == "c" and vb[0] == "c":
+                            return ("cb", "({} {} {})".format(va[1], x.op, vb[1]))
+                        (alo, ahi), (blo, bhi) = lanes(va), lanes(vb)
+                        n = self.tmp()
+                        e("const bool {n}l = ({} {op} {}), {n}h = ({} {op} {});".format(
+                            alo, blo, ahi, bhi, n=n, op=x.op), 3)
+                        return ("b", n + "l", n + "h")
+                    if isinstance(x, ex.Logic):
+                        vs = [val(y) for y in x.args]
+                        if x.op == "not":
+                            lo, hi = lanes(vs[0])
+                            if vs[0][0] == "cb":
+                                return ("cb", "(!{})".format(lo))
+                            return ("b", "(!{})".format(lo), "(!{})".format(hi))
+                        j = " && " if x.op == "and" else " || "
+                        if all(v[0] == "cb" for v in vs):
+                            return ("cb", "(" + j.join(v[1] for v in vs) + ")")
+                        return ("b", "(" + j.join(lanes(v)[0] for v in vs) + ")",
+                                "(" + j.join(lanes(v)[1] for v in vs) + ")")
+                    if isinstance(x, ex.Select):
+                        vc, va, vb = val(x.cond), val(x.a), val(x.b)
+                        (clo, chi), (alo, ahi), (blo, bhi) = lanes(vc), lanes(va), lanes(vb)
+                        lo = "({} ? {} : {})".format(clo, alo, blo)
+                        hi = "({} ? {} : {})".format(chi, ahi, bhi)
+                        if va[0] in ("b", "cb") and vb[0] in ("b", "cb"):
+                            return ("b", lo, hi)
+                        if vc[0] == "cb" and va[0] == "c" and vb[0] == "c":
+                            return ("c", lo)
+                        return new_pair(lo, hi)
+                    if isinstance(x, ex.Call):
+                        vs = [val(y) for y in x.args]
+                        if all(v[0] == "c" for v in vs):
+                            return ("c", "{}({})".format(math_fn[x.fn], ", ".join(v[1] for v in vs)))
+                        return new_pair("{}({})".format(math_fn[x.fn], ", ".join(lanes(v)[0] for v in vs)),
+                                        "{}({})".format(math_fn[x.fn], ", ".join(lanes(v)[1] for v in vs)))
+                    raise TypeError(type(x))
+
+                def fma(x):
+                    """a*b + c, c + a*b, a*b - c (c uniform), c - a*b (a or b uniform) as one FFMA2."""
+                    for mul, other, mul_first in ((x.a, x.b, True), (x.b, x.a, False)):
+                        if not (isinstance(mul, ex.Bin) and mul.op == "*"):
+                            continue
+                        if isinstance(other, ex.Bin) and other.op == "*" and not mul_first:
+                            continue
+                        ma, mb, vo = val(mul.a), val(mul.b), val(other)
+                        if not packable(ma, mb, vo) or (ma[0] == "c" and mb[0] == "c"):
+                            # evaluate the conventional way from the values already emitted
+                            vm = (("c", "({} * {})".format(ma[1], mb[1])) if ma[0] == "c" and mb[0] == "c" else
+                                  packed("sf_mul2", ma, mb) if packable(ma, mb) else
+                                  new_pair("({} * {})".format(lanes(ma)[0], lanes(mb)[0]),
+                                           "({} * {})".format(lanes(ma)[1], lanes(mb)[1])))
+                            va, vb = (vm, vo) if mul_first else (vo, vm)
+                            if va[0] == "c" and vb[0] == "c":
+                                return ("c", "({} {} {})".format(va[1], x.op, vb[1]))
+                            if packable(va, vb):
+                                return packed("sf_add2" if x.op == "+" else "sf_sub2", va, vb)
+                            (alo, ahi), (blo, bhi) = lanes(va), lanes(vb)
+                            return new_pair("({} {} {})".format(alo, x.op, blo), "({} {} {})".format(ahi, x.op, bhi))
+                        if x.op == "+":
+                            return packed("sf_fma2", ma, mb, vo)
+                        if mul_first:                       # a*b - c
+                            if vo[0] == "c":
+                                return packed("sf_fma2", ma, mb, negc(vo))
+                            return packed("sf_sub2", packed("sf_mul2", ma, mb), vo)
+                        if ma[0] == "c":                    # c - a*b
+                            return packed("sf_fma2", negc(ma), mb, vo)
+                        if mb[0] == "c":
+                            return packed("sf_fma2", ma, negc(mb), vo)
+                        return packed("sf_sub2", vo, packed("sf_mul2", ma, mb))
+                    return None
+
+                for s in op.statements:
+                    local[s.target] = val(s.value)
+                target = op.name if op.name in local else op.statements[-1].target
+                v = local[target]
+                dst = "nv[{}][{}]".format(r, h)
+                if v[0] == "p":
+                    e("{} = {};".format(dst, v[1]), 3)
+                elif v[0] == "c":
+                    e("{0} = make_float2({1}, {1});".format(dst, v[1]), 3)
+                else:
+                    lo, hi = lanes(v)
+                    e("{d}.x = {lo}; {d}.y = {hi};".format(d=dst, lo=lo, hi=hi), 3)
+
+    def _emit_shifts(self, src, vec, tag, rr, age, nl, nr, u):
         """Left/right neighbour cells of an owned row: warp shuffles, plus the column ring at warp
         edges when several warps share a row."""
         g, e, T, V = self.geo, self.emit, self.T, self.geo.V
@@ -666,30 +1135,30 @@ class StreamKernelGen:
         if nl:
             e("{T} l_{tag}[{n}];".format(T=T, tag=tag, n=nl), 3)
             for q in range(nl):
-                e("l_{tag}[{q}] = __shfl_up_sync(0xffffffffu, {vec}[{c}], 1);".format(
-                    tag=tag, q=q, vec=vec, c=V - nl + q), 3)
+                e("l_{tag}[{q}] = __shfl_up_sync(0xffffffffu, {c}, 1);".format(
+                    tag=tag, q=q, c=self.cellref(vec, V - nl + q)), 3)
         if nr:
             e("{T} g_{tag}[{n}];".format(T=T, tag=tag, n=nr), 3)
             for q in range(nr):
-                e("g_{tag}[{q}] = __shfl_down_sync(0xffffffffu, {vec}[{c}], 1);".format(
-                    tag=tag, q=q, vec=vec, c=q), 3)
+                e("g_{tag}[{q}] = __shfl_down_sync(0xffffffffu, {c}, 1);".format(
+                    tag=tag, q=q, c=self.cellref(vec, q)), 3)
         if src.col_ring and (nl or nr):
-            slot = self._slot_expr("xc_" + f, src.col_ring, age)
-            sz = g.R * V
+            slot = self.ring_slot("xc_" + f, src.col_ring, age, u)
+            n = src.col_reach
+            sz = g.R * n
+            # every lane reads the (broadcast) ring word, lanes at the warp edge keep it: no branch
             if nl:
-                e("if (lane == 0 && wc > 0) {", 3)
-                base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + wc - 1) * 2 + 1) * {sz} + {o}".format(
-                    f=f, slot=slot, WR=g.WR, WC=g.WC, sz=sz, o=rr * V)
+                base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + max(wc - 1, 0)) * 2 + 1) * {sz} + {o}".format(
+                    f=f, slot=slot, WR=g.WR, WC=g.WC, sz=sz, o=rr * n)
                 for q in range(nl):
-                    e("l_{tag}[{q}] = ({base})[{c}];".format(tag=tag, q=q, base=base, c=V - nl + q), 4)
-                e("}", 3)
+                    e("{{ const {T} rv = ({base})[{c}]; if (lane == 0 && wc > 0) l_{tag}[{q}] = rv; }}".format(
+                        T=T, tag=tag, q=q, base=base, c=n - nl + q), 3)
             if nr:
-                e("if (lane == 31 && wc < {}) {{".format(g.WC - 1), 3)
-                base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + wc + 1) * 2) * {sz} + {o}".format(
-                    f=f, slot=slot, WR=g.WR, WC=g.WC, sz=sz, o=rr * V)
+                base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + min(wc + 1, {last})) * 2) * {sz} + {o}".format(
+                    f=f, slot=slot, WR=g.WR, WC=g.WC, last=g.WC - 1, sz=sz, o=rr * n)
                 for q in range(nr):
-                    e("g_{tag}[{q}] = ({base})[{c}];".format(tag=tag, q=q, base=base, c=q), 4)
-                e("}", 3)
+                    e("{{ const {T} rv = ({base})[{c}]; if (lane == 31 && wc < {lastw}) g_{tag}[{q}] = rv; }}".format(
+                        T=T, tag=tag, q=q, base=base, c=q, lastw=g.WC - 1), 3)
 
     def _var(self, name, local, op):
         if name in local:
@@ -706,64 +1175,60 @@ class StreamKernelGen:
 # ---------------------------------------------------------------------------------- planning
 
 
-def _vector_width(program, dtype):
+def register_limit(threads):
+    """Registers per thread a single resident CTA of ``threads`` threads can have: each of the four
+    SM sub-partitions holds 16384 registers and ceil(warps / 4) of the CTA's warps."""
+    warps = -(-threads // 32)
+    return min(255, (16384 // (-(-warps // 4) * 32)) // 8 * 8)
+
+
+def _vector_width(program, dtype, options=None):
+    """Consecutive cells a thread owns along the innermost dimension: 16 bytes by default (one
+    128-bit shared-memory load / global store per row); ``options.vector`` asks for a longer run."""
     v = 16 // dtype.bytes
+    want = getattr(options, "vector", 0) or v
+    if want > v and want % v == 0 and program.shape[-1] % (want * 32) == 0:
+        v = want
     return v if program.shape[-1] % v == 0 else None
 
 
-def choose_geometry(program, ops, options) -> Optional[Tuple[GroupAnalysis, Geometry]]:
-    """Pick (V, R, warps, prefetch) for a candidate group or return None when it cannot stream."""
+def candidate_geometries(program, ops, options):
+    """(R, row groups, column warps, threads per row) candidates for a group, most specific first.
+    Explicit ``rows_per_thread`` / ``warps`` options restrict the list."""
     dtype = ops[0].data_type
     ndim = len(program.shape)
-    try:
-        V = _vector_width(program, dtype)
-        if V is None:
-            raise NotStreamable("innermost extent not a multiple of the vector width")
-        prefetch = options.prefetch or 2
-        candidates = []
-        nk = program.shape[-1]
-        if ndim == 3:
-            warps = options.warps or 16
-            rows = [options.rows_per_thread] if options.rows_per_thread else [4, 3, 2, 1]
+    V = _vector_width(program, dtype, options)
+    if V is None:
+        return V, []
+    nk = program.shape[-1]
+    out = []
+    if ndim == 3:
+        rows = [options.rows_per_thread] if options.rows_per_thread else [4, 3, 2, 1]
+        warps = [options.warps] if options.warps else [16, 12, 8]
+        for R in rows:
+            for w in warps:
+                out.append((R, w, 1, 32))
+        if nk < 32 * V and nk // V <= 64:
+            # narrow innermost dimension: one row of nk/V threads, several row groups per warp
+            ks = nk // V
             for R in rows:
-                candidates.append((R, warps, 1, 32))
-            if nk < 32 * V and nk // V <= 64:
-                # narrow innermost dimension: one row of nk/V threads, several row groups per warp
-                ks = nk // V
-                for R in rows:
-                    for groups in (options.warps * 32 // ks if options.warps else 0, 32, 24, 16):
-                        if groups and (groups * ks) % 32 == 0 and groups * ks <= 768:
-                            candidates.append((R, groups, 1, ks))
-        else:
-            warps = options.warps or 8
-            candidates.append((1, 1, warps, 32))
-        best = None
-        for (R, WR, WC, KS) in candidates:
-            try:
-                ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                geo = Geometry(ana, V, R, WR, WC, prefetch, KS)
-            except NotStreamable:
-                continue
-            if geo.smem > SMEM_LIMIT:
-                continue
-            if ana.window_registers(R, V) > REG_BUDGET:
-                continue
-            eff = (geo.BJ * geo.BK) / float(geo.TR * geo.TC) if ndim == 3 else geo.BK / float(geo.TC)
-            eff *= min(1.0, nk / float(geo.BK))          # lanes beyond a narrow domain are idle
-            if best is None or eff > best[0] + 1e-9:
-                best = (eff, ana, geo)
-        if best is None:
-            return None
-        return best[1], best[2]
-    except NotStreamable:
-        return None
+                for groups in ([options.warps * 32 // ks] if options.warps else [32, 24, 16, 12, 8]):
+                    if groups and (groups * ks) % 32 == 0 and groups * ks <= 768:
+                        out.append((R, groups, 1, ks))
+    else:
+        for w in ([options.warps] if options.warps else [8, 16]):
+            out.append((1, 1, w, 32))
+    return V, out
 
 
-# Cost model of the planner (seconds).  Calibrated on B200 (profiles/sweep_depth_rows_r01.txt):
-# a streamed pass costs max(HBM time of its algorithmic bytes, issue time of the cells it computes
-# including the redundant halo cells).
-HBM_BYTES_PER_S = 6.4e12
-UPDATES_PER_S = {4: 1.9e12, 8: 0.9e12}      # computed cell updates per second, by element size
+# Cost model of the planner (seconds), calibrated on B200 (profiles/r01_sweeps.txt): a streamed pass
+# costs max(HBM time of its algorithmic bytes, time to compute its cells incl. the redundant halo
+# cells).  The compute rate depends on the rows a thread owns (fewer rows = more exchange traffic per
+# cell through shared memory, the co-limiter of the fused kernels) and collapses when the register
+# windows do not fit the register file of the chosen CTA size.
+HBM_BYTES_PER_S = 6.1e12
+UPDATES_PER_S = {4: 2.7e12, 8: 0.95e12}     # computed cell updates per second at R = 4, by element size
+ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0}
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
 
 
@@ -773,20 +1238,56 @@ def _tile_efficiency(ana, geo):
     return geo.BK / float(geo.TC)
 
 
-def group_cost(program, ops, options):
-    """Estimated time of one streamed pass over ``ops`` (None if the group cannot stream)."""
-    chosen = choose_geometry(program, ops, options)
-    if chosen is None:
-        return None
-    ana, geo = chosen
+def modelled_time(program, ops, ana, geo):
     fields = program.fields
     nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields)
     nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
     eff = _tile_efficiency(ana, geo)
     used = min(1.0, program.shape[-1] / float(geo.BK))
     t_mem = nbytes / HBM_BYTES_PER_S
-    t_cmp = program.cells * len(ops) / (eff * used) / UPDATES_PER_S[ana.dtype.bytes]
+    rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), UPDATES_PER_S[ana.dtype.bytes]))
+    rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else 1.0
+    t_cmp = program.cells * len(ops) / (eff * used) / rate
     return max(t_mem, t_cmp) + 5e-6
+
+
+def choose_geometry(program, ops, options):
+    """Pick (V, R, warps, prefetch) for a candidate group -- the admissible geometry with the lowest
+    modelled pass time -- or return None when the group cannot stream."""
+    try:
+        V, candidates = candidate_geometries(program, ops, options)
+        if V is None:
+            raise NotStreamable("innermost extent not a multiple of the vector width")
+        prefetch = options.prefetch or 2
+        best = None
+        explicit = bool(options.rows_per_thread and options.warps)
+        for (R, WR, WC, KS) in candidates:
+            try:
+                ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
+                geo = Geometry(ana, V, R, WR, WC, prefetch, KS)
+            except NotStreamable:
+                continue
+            if geo.smem > SMEM_LIMIT:
+                continue
+            if not explicit and ana.register_estimate(R, V) > register_limit(geo.NT) + REG_SLACK:
+                continue
+            t = modelled_time(program, ops, ana, geo)
+            if best is None or t < best[0] * (1 - 1e-6):
+                best = (t, ana, geo)
+        if best is None:
+            return None
+        return best[1], best[2]
+    except NotStreamable:
+        return None
+
+
+def group_cost(program, ops, options):
+    """Estimated time of one streamed pass over ``ops`` (None if the group cannot stream)."""
+    chosen = choose_geometry(program, ops, options)
+    if chosen is None:
+        return None
+    ana, geo = chosen
+    return modelled_time(program, ops, ana, geo)
 
 
 def general_cost(program, op):
@@ -800,7 +1301,7 @@ def partition(program: StencilProgram, options):
     (dynamic programme over contiguous groups of at most ``max_depth`` operators)."""
     ops = list(program.ops)
     n = len(ops)
-    max_depth = options.max_depth or 8
+    max_depth = options.max_depth or 8          # explicit requests may go deeper
     best = [0.0] + [None] * n          # best[k]: cost of the first k operators
     choice = [None] * (n + 1)
     cache = {}
@@ -900,9 +1401,10 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                         info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "threads_per_row": geo.KS,
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
-                              "prefetch": geo.P, "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "prefetch": geo.P, "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
+                              "register_estimate": ana.register_estimate(geo.R, geo.V),
                               "stream_overhead_planes": overhead,
                               "back": max(i.back for i in ana.fields.values()),
                               "reach": {i.name: (i.back, i.fwd) for i in ana.ext_fields},

@@ -21,6 +21,8 @@ pass boundary is written to and re-read from HBM (slow memory).  The planner the
 the generated source).
 """
 
+import hashlib
+import json
 import os
 from typing import Dict, List, Optional
 
@@ -28,12 +30,46 @@ from . import lower_cuda
 from .stencil_op import StencilProgram
 
 
+TUNED_PLANS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_plans.json")
+
+
+def structure_key(program: StencilProgram) -> str:
+    """Hash of what determines the best plan: extents, and per operator its type, taps and boundary
+    handling -- with fields named by position, so renaming a program's fields keeps its entry."""
+    order = {name: n for n, name in enumerate(program.fields)}
+    ops = []
+    for op in program.ops:
+        taps = sorted((order[f], tuple(map(tuple, op.offsets3(f)))) for f in op.accesses)
+        bcs = sorted((order[f], bc.get("btype"), repr(bc.get("value"))) for f, bc in op.boundary_conditions.items()
+                     if f in order)
+        ops.append((op.data_type.name, taps, bcs, len(op.statements)))
+    text = json.dumps([list(program.shape), ops], default=str)
+    return hashlib.sha1(text.encode()).hexdigest()[:16]
+
+
+def load_tuned():
+    """The table ``scripts/tune.py`` measures on a B200: structure key -> plan options."""
+    try:
+        with open(TUNED_PLANS) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 class PlanOptions:
-    """Knobs, all overridable through ``SFB200_*`` environment variables."""
+    """Knobs, all overridable through ``SFB200_*`` environment variables.  When neither the caller
+    nor the environment sets any of them, ``plan_program`` looks the program up in the table of
+    measured plans (``tuned_plans.json``) before falling back on the cost model."""
+
+    KNOBS = ("SFB200_FUSE", "SFB200_MAX_DEPTH", "SFB200_ROWS", "SFB200_WARPS", "SFB200_CHUNK", "SFB200_PREFETCH",
+             "SFB200_VEC")
 
     def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
-                 prefetch=None):
+                 prefetch=None, vector=None):
         env = os.environ
+        self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector))
+                           and not any(k in env for k in self.KNOBS) and env.get("SFB200_TUNED", "1") != "0")
+        self.vector = int(env.get("SFB200_VEC", "0")) if vector is None else vector
         self.fuse = (env.get("SFB200_FUSE", "1") != "0") if fuse is None else fuse
         self.max_depth = int(env.get("SFB200_MAX_DEPTH", "0")) if max_depth is None else max_depth
         self.rows_per_thread = int(env.get("SFB200_ROWS", "0")) if rows_per_thread is None else rows_per_thread
@@ -42,7 +78,7 @@ class PlanOptions:
         self.prefetch = int(env.get("SFB200_PREFETCH", "0")) if prefetch is None else prefetch
 
     def as_dict(self):
-        return dict(self.__dict__)
+        return {k: v for k, v in self.__dict__.items() if k != "is_default"}
 
 
 class Plan:
@@ -120,6 +156,7 @@ class Plan:
             "operators": len(self.program.ops),
             "cell_updates": self.cell_updates(),
             "options": self.options.as_dict(),
+            "tuned_from": getattr(self, "tuned_from", None),
             "passes": [
                 {
                     "family": l.family, "kernel": l.kernel, "ops": l.ops, "reads": l.reads,
@@ -137,6 +174,12 @@ class Plan:
 def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
                  specialize=None) -> Plan:
     options = options or PlanOptions()
+    tuned_from = None
+    if options.is_default:
+        entry = load_tuned().get(structure_key(program))
+        if entry:
+            options = PlanOptions(**entry["options"])
+            tuned_from = entry.get("measured")
     lowered = lower_cuda.LoweredProgram(program)
     passes = []
     groups = None
@@ -158,4 +201,6 @@ def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
             from . import lower_stream
             lower_stream.lower_group(lowered, ops, options, specialize)
             passes.append({"family": "streamed", "ops": [op.name for op in ops]})
-    return Plan(program, lowered, passes, options)
+    plan = Plan(program, lowered, passes, options)
+    plan.tuned_from = tuned_from
+    return plan
