@@ -170,11 +170,14 @@ class CudaProgram:
             self._graph = None
 
     def _build_packs(self):
-        packs = []
         s_base, s_begin, s_end = self._slab_range()
-        for l in self.lowered.launches:
+        self._packs = [self._pack_launch(l, s_base, s_begin, s_end) for l in self.lowered.launches]
+
+    def _pack_launch(self, l, s_base, s_begin, s_end):
+        """(launch, function, grid, parameter pack) of launch ``l`` producing planes
+        [s_begin, s_end) of the slab axis, device buffers starting at plane ``s_base``."""
+        if True:
             vals = []
-            keep = []
             b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
             for a in l.args:
                 if a[0] == "buf":
@@ -206,8 +209,7 @@ class CudaProgram:
                 else:
                     raise ValueError(a)
             pack = rt.pack_params(vals)
-            packs.append((l, self.functions[l.kernel], l.grid_fn(b0, e0), pack))
-        self._packs = packs
+            return (l, self.functions[l.kernel], l.grid_fn(b0, e0), pack)
 
     def execute(self, stream=None):
         """Enqueue every launch of the plan (asynchronous)."""
@@ -275,10 +277,137 @@ class CudaProgram:
                 arrays[name] = val
         return arrays, scalars
 
+    # ------------------------------------------------------------------ pipelined host call
+    PIPELINE_MIN_BYTES = 64 << 20
+
+    def _pipeline_schedule(self, pieces):
+        """Cuts one execution into ``pieces`` along the slab axis so that host->device copies, the
+        passes and device->host copies of different pieces overlap (PCIe is full duplex).
+
+        Piece s makes input planes < e_s available; every launch then advances as far as the planes
+        it reads allow (its output frontier trails its inputs' by its forward reach), so nothing is
+        computed twice and no launch reads a plane that is not final.  Returns None when the plan
+        cannot be cut: no slab axis, an array that does not span it, or intermediates that share
+        storage (a later piece would still need planes an earlier piece's successor overwrote)."""
+        lowered = self.lowered
+        axis = lowered.slab_axis
+        if axis is None or self.slab is not None or pieces < 2:
+            return None
+        it = "ijk"[axis]
+        fields = self.program.fields
+        n = self.program.shape3[axis]
+        arrays = [name for name, f in fields.items() if not f.is_scalar and f.kind in ("input", "output")]
+        if any(it not in fields[a].dims or fields[a].dims[0] != it for a in arrays):
+            return None
+        assign = self.plan.buffer_assignment()
+        if len(set(assign.values())) != len(assign):
+            return None
+        from .distributed import launch_reach
+        reach = [launch_reach(lowered, idx) for idx in range(len(lowered.launches))]
+        if n // pieces < 4 * max([1] + [max(r) for rr in reach for r in rr.values()]):
+            return None
+        inputs = [a for a in arrays if fields[a].kind == "input"]
+        outputs = [a for a in arrays if fields[a].kind == "output"]
+        avail = {a: 0 for a in inputs}
+        done = [0] * len(lowered.launches)
+        out_done = {o: 0 for o in outputs}
+        schedule = []
+        for s in range(pieces):
+            e_in = (n * (s + 1)) // pieces
+            step = {"h2d": [], "launch": [], "d2h": []}
+            for a in inputs:
+                step["h2d"].append((a, avail[a], e_in))
+                avail[a] = e_in
+            for idx, l in enumerate(lowered.launches):
+                lim = n
+                for f in l.reads:
+                    if f not in avail:
+                        continue
+                    have = avail[f]
+                    fwd = reach[idx].get(f, (0, 0))[1]
+                    lim = min(lim, n if have >= n else have - fwd)
+                lim = max(lim, done[idx])
+                if lim > done[idx]:
+                    step["launch"].append(self._pack_launch(l, 0, done[idx], lim))
+                    done[idx] = lim
+                for f in l.writes:
+                    avail[f] = lim
+            for o in outputs:
+                if avail.get(o, 0) > out_done[o]:
+                    step["d2h"].append((o, out_done[o], avail[o]))
+                    out_done[o] = avail[o]
+            schedule.append(step)
+        assert all(d == n for d in done) and all(v == n for v in out_done.values())
+        return schedule
+
+    def _call_pipelined(self, arrays, pieces):
+        key = ("pipeline", pieces)
+        if getattr(self, "_pipe_key", None) != key or self._packs is None:
+            if self._packs is None:
+                self._build_packs()
+            self._pipe = self._pipeline_schedule(pieces)
+            self._pipe_key = key
+            if self._pipe is not None and not hasattr(self, "_pipe_streams"):
+                self._pipe_streams = (self.rt.stream_create(), self.rt.stream_create())
+                self._pipe_events = [(self.rt.event_create(False), self.rt.event_create(False))
+                                     for _ in range(pieces)]
+        if self._pipe is None:
+            return False
+        rtm, fields = self.rt, self.program.fields
+        s_in, s_out = self._pipe_streams
+        flat = {}
+        for name, arr in arrays.items():
+            f = fields[name]
+            arr = np.asarray(arr)
+            if arr.dtype != f.data_type.type or not arr.flags["C_CONTIGUOUS"] or arr.size != int(np.prod(f.shape)):
+                return False
+            flat[name] = arr.reshape(-1)
+        start = rtm.event_create(False)
+        rtm.event_record(start)                    # copies must not overtake earlier work on the main stream
+        rtm.stream_wait_event(s_in, start)
+        rtm.stream_wait_event(s_out, start)
+        for step, (ev_in, ev_done) in zip(self._pipe, self._pipe_events):
+            for (name, b, e) in step["h2d"]:
+                f = fields[name]
+                plane = int(np.prod(f.shape[1:])) if len(f.shape) > 1 else 1
+                if e > b:
+                    rtm.h2d(self.buffers[name].dptr + b * plane * f.data_type.bytes,
+                            flat[name][b * plane:e * plane], stream=s_in)
+            rtm.event_record(ev_in, s_in)
+            rtm.stream_wait_event(None, ev_in)
+            for l, fn, grid, pack in step["launch"]:
+                rtm.launch(fn, grid, l.block, l.smem, pack.array, None)
+            self.launch_count += len(step["launch"])
+            rtm.event_record(ev_done)
+            rtm.stream_wait_event(s_out, ev_done)
+            for (name, b, e) in step["d2h"]:
+                f = fields[name]
+                plane = int(np.prod(f.shape[1:])) if len(f.shape) > 1 else 1
+                rtm.d2h(flat[name][b * plane:e * plane],
+                        self.buffers[name].dptr + b * plane * f.data_type.bytes, stream=s_out)
+        rtm.stream_synchronize(s_out)
+        rtm.stream_synchronize()
+        rtm.event_destroy(start)
+        return True
+
     def __call__(self, **kwargs):
-        """Run once with host arrays: copy inputs in, execute, copy outputs back in place."""
+        """Run once with host arrays: copy inputs in, execute, copy outputs back in place.  Large
+        programs are cut into pieces along the outermost dimension so that the copies of one piece
+        overlap the passes and the copies of its neighbours (``SFB200_PIPELINE_PIECES``, 0 = off)."""
         arrays, scalars = self._split_call_args(kwargs)
         fields = self.program.fields
+        pieces = int(os.environ.get("SFB200_PIPELINE_PIECES", "16"))
+        in_out = [n for n, f in fields.items() if not f.is_scalar and f.kind in ("input", "output")]
+        if (pieces > 1 and self.synthetic_reads is None and all(n in arrays for n in in_out)
+                and sum(fields[n].nbytes for n in in_out) >= self.PIPELINE_MIN_BYTES):
+            need = [n for n, f in fields.items() if f.is_scalar]
+            missing = [n for n in need if n not in scalars and n not in self.scalar_values]
+            if missing:
+                raise KeyError("scalar input(s) {} were not provided".format(missing))
+            if scalars:
+                self.set_scalars(scalars)
+            if self._call_pipelined(arrays, pieces):
+                return
         for name, f in fields.items():
             if f.kind == "input" and not f.is_scalar:
                 if self.synthetic_reads is not None:

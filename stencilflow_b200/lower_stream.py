@@ -378,6 +378,8 @@ class Geometry:
                 raise NotStreamable("row reach exceeds rows per thread")
             if i.col_reach > V:
                 raise NotStreamable("column reach exceeds the vector width")
+        if self.TR > 256:
+            raise NotStreamable("tile taller than a TMA box")
         self.box_cols = min(self.TC, 256)
         if self.TC % self.box_cols:
             raise NotStreamable("tile width not a multiple of the TMA box")
@@ -1301,7 +1303,21 @@ def partition(program: StencilProgram, options):
     (dynamic programme over contiguous groups of at most ``max_depth`` operators)."""
     ops = list(program.ops)
     n = len(ops)
-    max_depth = options.max_depth or 8          # explicit requests may go deeper
+    if options.max_depth:
+        # an explicit depth is a request, not a bound: the longest streamable run of at most that
+        # many operators, repeatedly (what the tuner and the SFB200_MAX_DEPTH sweeps ask for)
+        groups, start = [], 0
+        while start < n:
+            for depth in range(min(options.max_depth, n - start), 0, -1):
+                group = ops[start:start + depth]
+                if group_cost(program, group, options) is not None:
+                    groups.append(("streamed", group))
+                    break
+                if depth == 1:
+                    groups.append(("general", group))
+            start += len(groups[-1][1])
+        return groups
+    max_depth = 8
     best = [0.0] + [None] * n          # best[k]: cost of the first k operators
     choice = [None] * (n + 1)
     cache = {}

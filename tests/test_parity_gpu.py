@@ -172,3 +172,104 @@ def test_size_independent_properties_at_scale(gpu):
     p(a_host=a, b7_host=out)
     p.close()
     assert rn.max_relative_error(expected, out) <= 1e-5
+
+
+PLAN_VARIANTS = [
+    # (max_depth, rows_per_thread, warps, vector): every CTA shape / fusion depth the planner or the
+    # tuner may pick, forced here on small programs so that each code shape is checked against the oracle
+    (1, 4, 16, 0), (2, 4, 16, 0), (2, 3, 12, 0), (3, 4, 12, 0), (4, 4, 8, 0), (4, 2, 16, 0), (3, 1, 8, 0),
+    (8, 2, 8, 0),
+]
+
+
+@pytest.mark.parametrize("variant", PLAN_VARIANTS, ids=lambda v: "d{}r{}w{}v{}".format(*v))
+@pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "jacobi3d_16x24x32_5itr_const1",
+                                  "jacobi3d_24x20x40_4itr_shrink_f64", "hdiff_24x28x16", "fork_join_20x16x24",
+                                  "box3d_10x12x16"])
+def test_plan_variants_3d(gpu, name, variant):
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    d, r, w, v = variant
+    inputs = random_inputs(name, seed=23)
+    expected = rn.run_reference(program_path(name), inputs)
+    got, _ = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, vector=v))
+    _check(name, got, expected)
+
+
+@pytest.mark.parametrize("variant", [(1, 8, 0), (2, 8, 0), (4, 8, 0), (6, 16, 0), (4, 8, 4), (2, 16, 8), (3, 8, 8)],
+                         ids=lambda v: "d{}w{}v{}".format(*v))
+@pytest.mark.parametrize("name", ["jacobi2d_96x128_6itr_shrink_f64", "jacobi2d_64x64_4itr_const_f32",
+                                  "ref_jacobi2d_128x128", "wide2d_8x2048_5itr_f64", "wide2d_6x4096_4itr_f32"])
+def test_plan_variants_2d(gpu, name, variant, tmp_path):
+    """2-D programs: fusion depths, CTA widths and cells per thread (the wide programs are there so
+    that several CTAs and the longer per-thread runs actually occur)."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    d, w, v = variant
+    if name.startswith("wide2d"):
+        dims = {"wide2d_8x2048_5itr_f64": ([8, 2048], 5, "float64"), "wide2d_6x4096_4itr_f32": ([6, 4096], 4, "float32")}[name]
+        prog = programs.jacobi2d_chain(dims[0], dims[1], dtype=dims[2])
+        path = str(tmp_path / (name + ".json"))
+        with open(path, "w") as f:
+            json.dump(prog, f)
+        rng = np.random.default_rng(5)
+        inputs = {"a": rng.random(dims[0]).astype(dims[2])}
+        halo = dims[1]
+    else:
+        path = program_path(name)
+        inputs = random_inputs(name, seed=29)
+        halo = HALO.get(name, 0)
+    expected = rn.run_reference(path, inputs)
+    p = CudaProgram(path, plan_options=PlanOptions(max_depth=d, warps=w, vector=v))
+    info = rn.ProgramInfo(rn.load_program(path))
+    outs = {o: np.zeros(info.shape, dtype=info.field_type(o)) for o in info.outputs}
+    args = {k + "_host": val for k, val in inputs.items()}
+    args.update({k + "_host": val for k, val in outs.items()})
+    p(**args)
+    p.close()
+    for field, ref in expected.items():
+        err = rn.max_relative_error(rn.trim_halo(ref, halo), rn.trim_halo(outs[field], halo))
+        assert err <= TOL[ref.dtype.name], "{}:{} max rel err {}".format(name, field, err)
+
+
+@pytest.mark.parametrize("kind", ["jacobi3d", "hdiff", "jacobi2d"])
+def test_pipelined_host_call(gpu, kind, monkeypatch):
+    """The host-array call cut into pieces (copies overlapping the passes) gives bit-identical
+    results to the plain upload / execute / download sequence, and matches the oracle."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200 import programs, synthetic
+    from stencilflow_b200.cuda_program import CudaProgram
+    if kind == "jacobi3d":
+        prog, halo = programs.jacobi3d_chain([192, 160, 256], 8), 0
+        inputs = {"a": synthetic.fill_hash((192, 160, 256), np.float32, 1234)}
+    elif kind == "hdiff":
+        prog, halo = programs.hdiff([384, 256, 80]), 2
+        inputs = {"inp": synthetic.fill_hash((384, 256, 80), np.float32, 1, 1.0, 2.0),
+                  "coeff": synthetic.fill_hash((384, 256, 80), np.float32, 2, 0.0, 0.05)}
+    else:
+        prog, halo = programs.jacobi2d_chain([2048, 4096], 6), 6
+        inputs = {"a": synthetic.fill_hash((2048, 4096), np.float64, 7)}
+    path = programs.write_program(prog, "pipelined_" + kind)
+    info = rn.ProgramInfo(rn.load_program(path))
+    results = []
+    for pieces in ("0", "8"):
+        monkeypatch.setenv("SFB200_PIPELINE_PIECES", pieces)
+        p = CudaProgram(path)
+        monkeypatch.setattr(p, "PIPELINE_MIN_BYTES", 1 << 20)
+        outs = {o: np.zeros(info.shape, dtype=info.field_type(o)) for o in info.outputs}
+        args = {k + "_host": v for k, v in inputs.items()}
+        args.update({k + "_host": v for k, v in outs.items()})
+        p(**args)
+        p(**args)                                   # a second call reuses the schedule
+        if pieces != "0":
+            assert getattr(p, "_pipe", None) is not None, "the pipelined path was not taken"
+        p.close()
+        results.append(outs)
+    for o in info.outputs:
+        assert np.array_equal(results[0][o], results[1][o])
+    expected = rn.run_reference(path, inputs)
+    for field, ref in expected.items():
+        err = rn.max_relative_error(rn.trim_halo(ref, halo), rn.trim_halo(results[1][field], halo))
+        assert err <= TOL[ref.dtype.name]
