@@ -107,9 +107,10 @@ def tune(name, prog, table, budget_s):
     cells = float(np.prod(prog["dimensions"]))
     chosen = ({"max_depth": d, "vector": r, "warps": w} if len(prog["dimensions"]) == 2
               else {"max_depth": d, "rows_per_thread": r, "warps": w})
-    table[key] = {"program": name, "options": chosen,
+    entries = [e for e in table.get(key, []) if e.get("shape") != list(prog["dimensions"])]
+    table[key] = entries + [{"program": name, "shape": list(prog["dimensions"]), "options": chosen,
                   "measured": {"ms": round(ms, 4), "cell_updates_per_s": nops * cells / (ms * 1e-3),
-                               "candidates": len(results), "device": "B200"}}
+                               "candidates": len(results), "device": "B200"}}]
     print("  best: depth {} rows {} warps {} -> {:.3f} ms ({:.3e} updates/s)".format(
         d, r, w, ms, nops * cells / (ms * 1e-3)))
 

@@ -356,8 +356,9 @@ class Geometry:
         ``KS = NK / V`` threads and thread t owns row group t / KS ("flat lanes": no idle lanes)."""
         self.V, self.R, self.WR, self.WC, self.KS = V, R, WR, WC, KS
         self.NT = KS * WR * WC
-        if KS != 32 and (WC != 1 or self.NT % 32 or any(i.col_reach for i in ana.fields.values())):
-            raise NotStreamable("flat lanes need a single column tile and no k-taps")
+        ktaps = any(i.col_reach for i in ana.fields.values())
+        if KS != 32 and (WC != 1 or self.NT % 32 or (ktaps and KS not in (8, 16))):
+            raise NotStreamable("narrow rows need a single column tile (and a power-of-two width for k-taps)")
         if self.NT > 1024:
             raise NotStreamable("too many threads")
         self.TR, self.TC = WR * R, WC * KS * V
@@ -1137,13 +1138,13 @@ class StreamKernelGen:
         if nl:
             e("{T} l_{tag}[{n}];".format(T=T, tag=tag, n=nl), 3)
             for q in range(nl):
-                e("l_{tag}[{q}] = __shfl_up_sync(0xffffffffu, {c}, 1);".format(
-                    tag=tag, q=q, c=self.cellref(vec, V - nl + q)), 3)
+                e("l_{tag}[{q}] = __shfl_up_sync(0xffffffffu, {c}, 1, {w});".format(
+                    tag=tag, q=q, c=self.cellref(vec, V - nl + q), w=g.KS), 3)
         if nr:
             e("{T} g_{tag}[{n}];".format(T=T, tag=tag, n=nr), 3)
             for q in range(nr):
-                e("g_{tag}[{q}] = __shfl_down_sync(0xffffffffu, {c}, 1);".format(
-                    tag=tag, q=q, c=self.cellref(vec, q)), 3)
+                e("g_{tag}[{q}] = __shfl_down_sync(0xffffffffu, {c}, 1, {w});".format(
+                    tag=tag, q=q, c=self.cellref(vec, q), w=g.KS), 3)
         if src.col_ring and (nl or nr):
             slot = self.ring_slot("xc_" + f, src.col_ring, age, u)
             n = src.col_reach
@@ -1210,6 +1211,11 @@ def candidate_geometries(program, ops, options):
         for R in rows:
             for w in warps:
                 out.append((R, w, 1, 32))
+        if nk >= 32 * V:
+            # rows of 16 threads, two row groups per warp: a squarer tile (less halo to recompute)
+            for R in rows:
+                for w in warps:
+                    out.append((R, 2 * w, 1, 16))
         if nk < 32 * V and nk // V <= 64:
             # narrow innermost dimension: one row of nk/V threads, several row groups per warp
             ks = nk // V
@@ -1220,6 +1226,9 @@ def candidate_geometries(program, ops, options):
     else:
         for w in ([options.warps] if options.warps else [8, 16]):
             out.append((1, 1, w, 32))
+    ks = getattr(options, "threads_per_row", 0)
+    if ks:
+        out = [c for c in out if c[3] == ks]
     return V, out
 
 

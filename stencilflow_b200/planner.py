@@ -34,17 +34,50 @@ TUNED_PLANS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_pl
 
 
 def structure_key(program: StencilProgram) -> str:
-    """Hash of what determines the best plan: extents, and per operator its type, taps and boundary
-    handling -- with fields named by position, so renaming a program's fields keeps its entry."""
-    order = {name: n for n, name in enumerate(program.fields)}
-    ops = []
-    for op in program.ops:
-        taps = sorted((order[f], tuple(map(tuple, op.offsets3(f)))) for f in op.accesses)
-        bcs = sorted((order[f], bc.get("btype"), repr(bc.get("value"))) for f, bc in op.boundary_conditions.items()
-                     if f in order)
-        ops.append((op.data_type.name, taps, bcs, len(op.statements)))
-    text = json.dumps([list(program.shape), ops], default=str)
+    """Hash of the operator structure that determines the best plan, independent of names, extents
+    and chain length: the *set* of distinct operator signatures, an operator's signature being its
+    type, its boundary handling and its taps with each source named relative to the operator (the
+    n-th operator before it, or the n-th program input).  An 8- and a 64-stage chain of the same
+    stencil share a key; ``lookup_tuned`` then picks the entry with the closest extents."""
+    op_index = {op.name: n for n, op in enumerate(program.ops)}
+    inputs = [name for name, f in program.fields.items() if f.kind == "input"]
+
+    def rel(field, k):
+        if field in op_index:
+            return "op-{}".format(k - op_index[field])
+        return "in{}".format(inputs.index(field)) if field in inputs else field
+
+    sigs = set()
+    for k, op in enumerate(program.ops):
+        taps = sorted((rel(f, k), tuple(map(tuple, op.offsets3(f)))) for f in op.accesses)
+        bcs = sorted((rel(f, k), bc.get("btype"), repr(bc.get("value")))
+                     for f, bc in op.boundary_conditions.items() if f in op.accesses)
+        sigs.add(json.dumps([op.data_type.name, taps, bcs, len(op.statements)], default=str))
+    text = json.dumps([len(program.shape), sorted(sigs)])
     return hashlib.sha1(text.encode()).hexdigest()[:16]
+
+
+def lookup_tuned(program: StencilProgram, table=None):
+    """Entry of the measured-plan table for ``program``: same operator structure, and the extents
+    closest (in log distance) among the entries whose innermost dimension is in the same class
+    (narrow / wide) and whose cell count is within 64x.  None if there is none."""
+    import math
+    table = load_tuned() if table is None else table
+    entries = table.get(structure_key(program))
+    if not entries:
+        return None
+    shape = list(program.shape)
+    best = None
+    for entry in entries:
+        other = entry.get("shape")
+        if not other or len(other) != len(shape) or (other[-1] < 128) != (shape[-1] < 128):
+            continue
+        dist = sum(abs(math.log2(a / float(b))) for a, b in zip(shape, other))
+        if dist > 6.0:
+            continue
+        if best is None or dist < best[0]:
+            best = (dist, entry)
+    return best[1] if best else None
 
 
 def load_tuned():
@@ -62,14 +95,16 @@ class PlanOptions:
     measured plans (``tuned_plans.json``) before falling back on the cost model."""
 
     KNOBS = ("SFB200_FUSE", "SFB200_MAX_DEPTH", "SFB200_ROWS", "SFB200_WARPS", "SFB200_CHUNK", "SFB200_PREFETCH",
-             "SFB200_VEC")
+             "SFB200_VEC", "SFB200_KS")
 
     def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
-                 prefetch=None, vector=None):
+                 prefetch=None, vector=None, threads_per_row=None):
         env = os.environ
-        self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector))
+        self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector,
+                                                   threads_per_row))
                            and not any(k in env for k in self.KNOBS) and env.get("SFB200_TUNED", "1") != "0")
         self.vector = int(env.get("SFB200_VEC", "0")) if vector is None else vector
+        self.threads_per_row = int(env.get("SFB200_KS", "0")) if threads_per_row is None else threads_per_row
         self.fuse = (env.get("SFB200_FUSE", "1") != "0") if fuse is None else fuse
         self.max_depth = int(env.get("SFB200_MAX_DEPTH", "0")) if max_depth is None else max_depth
         self.rows_per_thread = int(env.get("SFB200_ROWS", "0")) if rows_per_thread is None else rows_per_thread
@@ -176,7 +211,7 @@ def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
     options = options or PlanOptions()
     tuned_from = None
     if options.is_default:
-        entry = load_tuned().get(structure_key(program))
+        entry = lookup_tuned(program)
         if entry:
             options = PlanOptions(**entry["options"])
             tuned_from = entry.get("measured")

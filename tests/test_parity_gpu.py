@@ -179,20 +179,24 @@ PLAN_VARIANTS = [
     # tuner may pick, forced here on small programs so that each code shape is checked against the oracle
     (1, 4, 16, 0), (2, 4, 16, 0), (2, 3, 12, 0), (3, 4, 12, 0), (4, 4, 8, 0), (4, 2, 16, 0), (3, 1, 8, 0),
     (8, 2, 8, 0),
+    # rows of 16 / 8 threads (two / four row groups per warp)
+    (2, 4, 8, 0, 16), (4, 4, 8, 0, 16), (3, 2, 12, 0, 16), (2, 3, 8, 0, 8),
 ]
 
 
-@pytest.mark.parametrize("variant", PLAN_VARIANTS, ids=lambda v: "d{}r{}w{}v{}".format(*v))
+@pytest.mark.parametrize("variant", PLAN_VARIANTS, ids=lambda v: "d{}r{}w{}v{}".format(*v[:4]) + ("" if len(v) < 5 else "k{}".format(v[4])))
 @pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "jacobi3d_16x24x32_5itr_const1",
                                   "jacobi3d_24x20x40_4itr_shrink_f64", "hdiff_24x28x16", "fork_join_20x16x24",
                                   "box3d_10x12x16"])
 def test_plan_variants_3d(gpu, name, variant):
     from oracle import reference_numpy as rn
     from stencilflow_b200.planner import PlanOptions
-    d, r, w, v = variant
+    d, r, w, v = variant[:4]
+    ks = variant[4] if len(variant) > 4 else 0
     inputs = random_inputs(name, seed=23)
     expected = rn.run_reference(program_path(name), inputs)
-    got, _ = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, vector=v))
+    got, prog = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, vector=v,
+                                                    threads_per_row=ks))
     _check(name, got, expected)
 
 
