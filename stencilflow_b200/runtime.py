@@ -305,7 +305,8 @@ class Runtime:
         _check(self.lib.sfb_event_synchronize(event))
 
     def stream_wait_event(self, stream, event):
-        _check(self.lib.sfb_stream_wait_event(stream, event))
+        """``stream`` None = the runtime's launch stream (not the legacy NULL stream)."""
+        _check(self.lib.sfb_stream_wait_event(self.stream if stream is None else stream, event))
 
     def elapsed_ms(self, start, stop):
         ms = ctypes.c_float(0)

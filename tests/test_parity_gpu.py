@@ -265,7 +265,10 @@ def test_pipelined_host_call(gpu, kind, monkeypatch):
         outs = {o: np.zeros(info.shape, dtype=info.field_type(o)) for o in info.outputs}
         args = {k + "_host": v for k, v in inputs.items()}
         args.update({k + "_host": v for k, v in outs.items()})
-        p(**args)
+        # first call with other data: the second call must not see anything stale on the device
+        other = {k + "_host": (v * v.dtype.type(0.5) + v.dtype.type(0.25)) for k, v in inputs.items()}
+        other.update({k + "_host": v for k, v in outs.items()})
+        p(**other)
         p(**args)                                   # a second call reuses the schedule
         if pieces != "0":
             assert getattr(p, "_pipe", None) is not None, "the pipelined path was not taken"
