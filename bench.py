@@ -303,10 +303,20 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(str(args.config), {}).get("dram_bytes_per_launch")
+            rec = json.load(f).get(str(args.config), {})
+            # the ncu capture only describes the kernel it was taken from
+            if rec.get("kernel") == program.lowered.launches[0].kernel and world == 1:
+                traffic = rec.get("dram_bytes_per_launch")
+    # fusion-independent companion figure: the program's minimum off-chip volume
+    # (every input read once, every output written once) over the same time
+    fields = program.program.fields
+    min_volume = sum(f.nbytes for f in fields.values() if f.kind in ("input", "output") and not f.is_scalar)
+    min_volume *= (1.0 if world == 1 else local_fraction)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_step / lps, "launches_per_step": lps,
+                "operators_per_launch": [len(l.ops) for l in program.lowered.launches],
+                "min_volume_frac": min_volume / (ms_local / args.steps * 1e-3) / 1e9 / peak_gbs,
                 "kernel": program.lowered.launches[0].kernel, "family": program.lowered.launches[0].family}
 
     # end to end through the plugin call with host buffers (pinned), copies inside the timed region
@@ -329,7 +339,7 @@ def main():
             "config": {"workload": workload_name(args.config, prog),
                        "per_gpu": "x".join(map(str, [prog["dimensions"][0] // world] + prog["dimensions"][1:])),
                        "l2": "no flush needed: every pass streams fields of {:.1f} GiB, far above the 126 MB L2".format(
-                           cells_total / world * 4 / 2 ** 30),
+                           cells_total / world * (8 if "float64" in json.dumps(prog["program"]) else 4) / 2 ** 30),
                        "plan": [{"family": l.family, "ops": len(l.ops)} for l in program.lowered.launches],
                        "input": "U[0,1) counter hash generated in HBM (seed 1234)"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
