@@ -37,6 +37,7 @@ from .lower_cuda import (KernelSpec, LaunchSpec, LoweredProgram, _MATH_F32, _MAT
 from .stencil_op import JUNK_VAL, StencilOp, StencilProgram
 
 SMEM_LIMIT = 227 * 1024
+DEFAULT_SYNC = "cta"        # "pair": neighbour-only named barriers + per-warp TMA staging (see Geometry)
 REG_SLACK = int(os.environ.get("SFB200_REG_SLACK", "0"))   # the estimate may exceed the per-thread limit by this much
 
 STREAM_PRELUDE = r"""
@@ -93,6 +94,25 @@ __device__ __forceinline__ void sf_tma_load_2d(void* dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// ---- neighbour-only synchronisation ("pair" mode) ----
+// Warp w exchanges data with warps w-1 and w+1 only, so instead of one CTA-wide barrier per streamed
+// plane it meets each neighbour at a 64-thread named barrier (id w for the pair (w-1, w)).  Even warps
+// meet their upper neighbour first, odd warps their lower one: all pairs (2n, 2n+1) meet concurrently,
+// then all pairs (2n+1, 2n+2) -- no ripple through the CTA, and warps that are not neighbours may
+// drift a step apart (the FPGA's processing elements handshake the same way, through their FIFOs).
+__device__ __forceinline__ void sf_bar_pair(int id) {
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void sf_sync_neighbours(int w) {
+    if (w & 1) {
+        sf_bar_pair(w);
+        if (w + 1 < NW) sf_bar_pair(w + 1);
+    } else {
+        if (w + 1 < NW) sf_bar_pair(w + 1);
+        if (w > 0) sf_bar_pair(w);
+    }
 }
 // ---- packed float32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a) ----
 __device__ __forceinline__ float2 sf_add2(float2 a, float2 b) {
@@ -350,7 +370,7 @@ class GroupAnalysis:
 
 
 class Geometry:
-    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32):
+    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32, sync="cta"):
         """``KS`` = threads per tile row.  32 (a warp per row, k-neighbours by shuffle) in general;
         for groups without k-taps on a narrow innermost dimension the whole extent is one row of
         ``KS = NK / V`` threads and thread t owns row group t / KS ("flat lanes": no idle lanes)."""
@@ -384,6 +404,23 @@ class Geometry:
         self.box_cols = min(self.TC, 256)
         if self.TC % self.box_cols:
             raise NotStreamable("tile width not a multiple of the TMA box")
+        # "pair" synchronisation: every warp loads its own part of each input plane (own TMA box, own
+        # mbarriers) and meets only its two neighbours once per plane.  Needs whole row groups per
+        # warp (3-D, one column of warps) or one row of warps (2-D), and one named barrier per pair.
+        nw = self.NT // 32
+        self.NW = nw
+        self.pair = False
+        if sync == "pair" and 2 <= nw <= 16:
+            if ana.ndim == 3 and WC == 1 and 32 % KS == 0 and self.TC <= 256:
+                self.pair = True
+                self.warp_rows = (32 // KS) * R
+                self.box = [self.TC, self.warp_rows, 1]
+            elif ana.ndim == 2 and WR == 1 and KS == 32 and 32 * V <= 256:
+                self.pair = True
+                self.warp_rows = 1
+                self.box = [32 * V, 1]
+        if not self.pair:
+            self.box = [self.box_cols, self.TR, 1] if ana.ndim == 3 else [self.box_cols, 1]
         self.smem = self._smem(ana)
 
     def _smem(self, ana):
@@ -404,7 +441,7 @@ class Geometry:
                 off += i.col_ring * self.WR * self.WC * 2 * self.R * i.col_reach * b
                 off = (off + 127) & ~127
         self.bar_off = off
-        off += 8 * self.D
+        off += 8 * self.D * (self.NW if self.pair else 1)
         return off
 
 
@@ -601,7 +638,7 @@ class StreamKernelGen:
                     T=T, f=self.fid[i.name], o=g.xcol_off[i.name]))
         e("unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.bar_off))
         e("if (threadIdx.x == 0) {")
-        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D), 2)
+        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D * (g.NW if g.pair else 1)), 2)
         e("sf_fence_barrier_init();", 2)
         e("}")
         e("__syncthreads();")
@@ -643,26 +680,48 @@ class StreamKernelGen:
         # copies themselves are issued by the first `issuers` warps, one box each per round
         issuers = 1 if total_boxes <= 2 else min(nwarps, nbox)
         e("const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform")
-        e("auto issue = [&](int t, int s) {")
-        e("if (warp_u == 0) sf_mbar_expect_tx(&bars[s], {});".format(tile_bytes * len(ext)), 2)
-        for n, i in enumerate(ext):
-            plane = "t - ({}) - s_base".format(i.lag)
-            if issuers == 1:
-                boxes = [str(b * g.box_cols) for b in range(nbox)]
-            else:
-                e("for (int b = warp_u; b < {}; b += {}) {{".format(nbox, issuers), 2)
-                boxes = ["b * {}".format(g.box_cols)]
-            for bo in boxes:
-                dst = "tile_{f} + s * {sz} + {bo}".format(f=self.fid[i.name], sz=g.TR * g.TC, bo=bo)
+        if g.pair:
+            # every warp stages its own rows (3-D) / columns (2-D) of the plane and owns the barriers
+            box_elems = g.box[0] * g.box[1]
+            e("unsigned long long* const wbars = bars + warp_u * {};".format(g.D))
+            e("auto issue = [&](int t, int s) {")
+            e("sf_mbar_expect_tx(&wbars[s], {});".format(box_elems * self.ct.bytes * len(ext)), 2)
+            for n, i in enumerate(ext):
+                plane = "t - ({}) - s_base".format(i.lag)
                 if ndim == 3:
-                    e("sf_tma_load_3d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, tile_j0 - {}, {});".format(
-                        dst, n, g.HK0, bo, g.HJ0, plane), 2)
+                    dst = "tile_{f} + s * {sz} + warp_u * {wsz}".format(f=self.fid[i.name], sz=g.TR * g.TC,
+                                                                       wsz=g.warp_rows * g.TC)
+                    e("sf_tma_load_3d({}, &tm_{}, &wbars[s], tile_k0 - {}, tile_j0 - {} + warp_u * {}, {});".format(
+                        dst, n, g.HK0, g.HJ0, g.warp_rows, plane), 2)
                 else:
-                    e("sf_tma_load_2d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, {});".format(
-                        dst, n, g.HK0, bo, plane), 2)
-            if issuers > 1:
-                e("}", 2)
-        e("};")
+                    dst = "tile_{f} + s * {sz} + warp_u * {wsz}".format(f=self.fid[i.name], sz=g.TR * g.TC,
+                                                                       wsz=g.box[0])
+                    e("sf_tma_load_2d({}, &tm_{}, &wbars[s], tile_k0 - {} + warp_u * {}, {});".format(
+                        dst, n, g.HK0, g.box[0], plane), 2)
+            e("};")
+            issuers = nwarps
+        else:
+            e("unsigned long long* const wbars = bars;")
+            e("auto issue = [&](int t, int s) {")
+            e("if (warp_u == 0) sf_mbar_expect_tx(&bars[s], {});".format(tile_bytes * len(ext)), 2)
+            for n, i in enumerate(ext):
+                plane = "t - ({}) - s_base".format(i.lag)
+                if issuers == 1:
+                    boxes = [str(b * g.box_cols) for b in range(nbox)]
+                else:
+                    e("for (int b = warp_u; b < {}; b += {}) {{".format(nbox, issuers), 2)
+                    boxes = ["b * {}".format(g.box_cols)]
+                for bo in boxes:
+                    dst = "tile_{f} + s * {sz} + {bo}".format(f=self.fid[i.name], sz=g.TR * g.TC, bo=bo)
+                    if ndim == 3:
+                        e("sf_tma_load_3d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, tile_j0 - {}, {});".format(
+                            dst, n, g.HK0, bo, g.HJ0, plane), 2)
+                    else:
+                        e("sf_tma_load_2d({}, &tm_{}, &bars[s], tile_k0 - {} + {}, {});".format(
+                            dst, n, g.HK0, bo, plane), 2)
+                if issuers > 1:
+                    e("}", 2)
+            e("};")
         e("const bool issuer = warp_u < {};".format(issuers))
         e("if (issuer && sf_elect_one()) {")
         e("for (int p = 0; p < {}; ++p) if (t_begin + p < t_end) issue(t_begin + p, p);".format(g.P), 2)
@@ -725,7 +784,7 @@ class StreamKernelGen:
             if self.pipeline and self._can_gather_early(self.ops[0]):
                 # neighbour data of the first operator is a step old: fetch it while the TMA lands
                 gathered[0] = self._gather_op(self.ops[0], u, 0)
-            e("sf_mbar_wait(&bars[{}], {});".format(self.slot_expr, ph), 2)
+            e("sf_mbar_wait(&wbars[{}], {});".format(self.slot_expr, ph), 2)
             for i in ext:
                 self._produce_ext(i, u)
             for k, op in enumerate(self.ops):
@@ -736,7 +795,10 @@ class StreamKernelGen:
                     # before this operator's arithmetic, which hides their latency
                     gathered[k + 1] = self._gather_op(self.ops[k + 1], u, k + 1)
                 self._produce_op(op, u, gathered.pop(k))
-            e("__syncthreads();", 2)
+            if g.pair:
+                e("sf_sync_neighbours<{}>(warp_u);".format(g.NW), 2)
+            else:
+                e("__syncthreads();", 2)
             if not static_d:
                 e("if (++slot == {}) {{ slot = 0; phase ^= 1; }}".format(g.D), 2)
             for i in a.fields.values():
@@ -747,10 +809,7 @@ class StreamKernelGen:
             e("}", 2)
 
     def _box(self):
-        g = self.geo
-        if self.ana.ndim == 3:
-            return [g.box_cols, g.TR, 1]
-        return [g.box_cols, 1]
+        return list(self.geo.box)
 
     # ------------------------------------------------------------------ producing a field
     def _open_plane(self, info: _FieldInfo, u: int):
@@ -1275,7 +1334,7 @@ def choose_geometry(program, ops, options):
         for (R, WR, WC, KS) in candidates:
             try:
                 ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                geo = Geometry(ana, V, R, WR, WC, prefetch, KS)
+                geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(options, "sync", "") or DEFAULT_SYNC)
             except NotStreamable:
                 continue
             if geo.smem > SMEM_LIMIT:
@@ -1426,7 +1485,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                         info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "threads_per_row": geo.KS,
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
-                              "prefetch": geo.P, "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "prefetch": geo.P, "sync": "pair" if geo.pair else "cta", "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "register_estimate": ana.register_estimate(geo.R, geo.V),

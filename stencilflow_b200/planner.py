@@ -95,13 +95,13 @@ class PlanOptions:
     measured plans (``tuned_plans.json``) before falling back on the cost model."""
 
     KNOBS = ("SFB200_FUSE", "SFB200_MAX_DEPTH", "SFB200_ROWS", "SFB200_WARPS", "SFB200_CHUNK", "SFB200_PREFETCH",
-             "SFB200_VEC", "SFB200_KS")
+             "SFB200_VEC", "SFB200_KS", "SFB200_SYNC")
 
     def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
-                 prefetch=None, vector=None, threads_per_row=None):
+                 prefetch=None, vector=None, threads_per_row=None, sync=None):
         env = os.environ
         self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector,
-                                                   threads_per_row))
+                                                   threads_per_row, sync))
                            and not any(k in env for k in self.KNOBS) and env.get("SFB200_TUNED", "1") != "0")
         self.vector = int(env.get("SFB200_VEC", "0")) if vector is None else vector
         self.threads_per_row = int(env.get("SFB200_KS", "0")) if threads_per_row is None else threads_per_row
@@ -111,6 +111,7 @@ class PlanOptions:
         self.warps = int(env.get("SFB200_WARPS", "0")) if warps is None else warps
         self.chunk = int(env.get("SFB200_CHUNK", "0")) if chunk is None else chunk
         self.prefetch = int(env.get("SFB200_PREFETCH", "0")) if prefetch is None else prefetch
+        self.sync = env.get("SFB200_SYNC", "") if sync is None else sync
 
     def as_dict(self):
         return {k: v for k, v in self.__dict__.items() if k != "is_default"}

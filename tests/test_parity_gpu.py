@@ -280,3 +280,65 @@ def test_pipelined_host_call(gpu, kind, monkeypatch):
     for field, ref in expected.items():
         err = rn.max_relative_error(rn.trim_halo(ref, halo), rn.trim_halo(results[1][field], halo))
         assert err <= TOL[ref.dtype.name]
+
+
+PAIR_VARIANTS_3D = [
+    # (max_depth, rows_per_thread, warps, threads per row, prefetch): neighbour-only synchronisation with
+    # per-warp TMA staging, and deeper TMA rings under both synchronisation schemes
+    (4, 4, 8, 16, 2, "pair"), (4, 4, 8, 32, 5, "pair"), (2, 4, 16, 32, 3, "pair"), (3, 3, 12, 16, 5, "pair"),
+    (4, 2, 16, 16, 2, "pair"), (1, 4, 8, 32, 2, "pair"), (4, 4, 8, 16, 5, "cta"), (3, 4, 12, 32, 3, "cta"),
+]
+
+
+@pytest.mark.parametrize("variant", PAIR_VARIANTS_3D, ids=lambda v: "d{}r{}w{}k{}p{}{}".format(*v))
+@pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "jacobi3d_16x24x32_5itr_const1",
+                                  "jacobi3d_24x20x40_4itr_shrink_f64", "fork_join_20x16x24", "box3d_10x12x16"])
+def test_pair_sync_and_prefetch_3d(gpu, name, variant):
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    d, r, w, ks, p, sync = variant
+    inputs = random_inputs(name, seed=31)
+    expected = rn.run_reference(program_path(name), inputs)
+    got, prog = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, threads_per_row=ks,
+                                                    prefetch=p, sync=sync))
+    _check(name, got, expected)
+
+
+def test_pair_sync_is_selected_when_asked(native_lib):
+    """The knob reaches the generator: the streamed launches of a chain report pair synchronisation."""
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    p = CudaProgram(program_path("ref_jacobi3d_32x32x32_8itr_8vec"), allocate=False,
+                    plan_options=PlanOptions(max_depth=4, rows_per_thread=4, warps=8, sync="pair"))
+    assert all(l.info["sync"] == "pair" for l in p.lowered.launches if l.family == "streamed")
+
+
+@pytest.mark.parametrize("kind", ["jacobi3d", "jacobi2d"])
+def test_pair_sync_bit_identical_at_scale(gpu, kind):
+    """Many CTAs, many waves: neighbour-only synchronisation with a deep TMA ring must reproduce the
+    CTA-barrier kernel bit for bit (same per-cell arithmetic; any race would show as a difference)."""
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    if kind == "jacobi3d":
+        prog, out, dt = programs.jacobi3d_chain([320, 448, 512], 8), "b7", np.float32
+        variants = [dict(max_depth=4, rows_per_thread=4, warps=8, sync="cta"),
+                    dict(max_depth=4, rows_per_thread=4, warps=8, sync="pair", prefetch=5),
+                    dict(max_depth=4, rows_per_thread=3, warps=12, sync="pair", prefetch=3)]
+    else:
+        prog, out, dt = programs.jacobi2d_chain([3000, 16384], 8), "b7", np.float64
+        variants = [dict(max_depth=8, vector=4, warps=8, sync="cta"),
+                    dict(max_depth=8, vector=4, warps=8, sync="pair", prefetch=5),
+                    dict(max_depth=4, vector=2, warps=16, sync="pair", prefetch=3)]
+    path = programs.write_program(prog, "pairsync_" + kind)
+    n = int(np.prod(prog["dimensions"]))
+    sums = []
+    for opts in variants:
+        p = CudaProgram(path, plan_options=PlanOptions(**opts))
+        p.rt.fill_hash(p.buffers["a"].dptr, n, dt, seed=99)
+        for _ in range(3):
+            p.execute()
+        p.rt.stream_synchronize()
+        sums.append(p.rt.checksum(p.buffers[out].dptr, n, dt))
+        p.close()
+    assert sums[1][1] == sums[0][1] and sums[2][1] == sums[0][1], sums
