@@ -54,7 +54,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -195,7 +195,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(rates), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": args.scaling or "weak", "vs_baseline": None,
         "dtype": "f64" if "f64" in name else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, prog)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -215,14 +215,22 @@ def workload_name(index, prog):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100,
+                    help="timed executions of the program (default 100: long enough for the clock "
+                         "sampler to see the load and for the power cap to show)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = every rank owns one copy of the config's domain (default for "
+                         "configs 1-3); strong = the config's domain is split (default for config 4, "
+                         "the 2048^3 x 64 slab-split case of BASELINE.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.scaling is None:
+        args.scaling = "strong" if args.config == 4 else "weak"
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -250,7 +258,7 @@ def main():
         from stencilflow_b200 import distributed
         comm = distributed.TorchComm()
 
-    name, prog, halo = build_config(args.config, scale_i=world)
+    name, prog, halo = build_config(args.config, scale_i=world if args.scaling == "weak" else 1)
     path = programs.write_program(prog, name)
     if world > 1:
         from stencilflow_b200 import distributed
@@ -333,7 +341,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if "float64" in json.dumps(prog["program"]) else "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args.config, prog),

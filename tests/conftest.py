@@ -46,6 +46,11 @@ HALO = {
 INPUT_RANGES = {
     "hdiff_24x28x16": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
     "hdiff_16x20x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
+    # hotspot: coefficients of a stable explicit step (the generator's default 0.5 is not)
+    "synth_hotspot2d_48x64_4st_f64": {"sdc": (0.05, 0.1), "r_x": (0.5, 1.0), "r_y": (0.5, 1.0), "r_z": (0.5, 1.0),
+                                      "amb": (0.5, 1.0)},
+    "synth_hotspot3d_12x12x16_4st": {s: (0.05, 0.15) for s in ("cc", "cn", "cs", "cw", "ce", "ca", "cb", "sdc")},
+    "synth_diffusion_10x12x16_4st": {"c%d" % n: (0.05, 0.25) for n in range(7)},
 }
 
 
@@ -62,7 +67,8 @@ def random_inputs(name, seed=7):
         dt = info.field_type(field)
         lo, hi = INPUT_RANGES.get(name, {}).get(field, (0.0, 1.0))
         if len(shape) == 0:
-            inputs[field] = dt(rng.uniform(0.5, 1.5))
+            slo, shi = INPUT_RANGES.get(name, {}).get(field, (0.5, 1.5))
+            inputs[field] = dt(rng.uniform(slo, shi))
         else:
             inputs[field] = rng.uniform(lo, hi, size=shape).astype(dt)
     return inputs

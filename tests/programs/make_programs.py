@@ -149,6 +149,18 @@ def main():
                   "boundary_conditions": {"b": {"type": "constant", "value": 0.0}}, "data_type": "float32"},
             "e": {"computation_string": "e = c[i,j,k] + d[i+1,j,k] + 0.5*d[i-1,j,k]",
                   "boundary_conditions": {"d": {"type": "constant", "value": 0.0}}, "data_type": "float32"}}})
+    # programs written by the synthetic generator (the reference's bin/synthesize.py conventions):
+    # box taps with extra off-chip fields, per-tap 0-D coefficients, the Rodinia hotspot formulas in
+    # 3-D and 2-D, and a chain with a fork and a join
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from stencilflow_b200 import synthesize as syn
+    dump("synth_box_12x10x16_3st", syn.synthesize("float32", 3, 0.5, 12, 10, 16, 1, 1, 1, stencil_shape="box"))
+    dump("synth_diffusion_10x12x16_4st", syn.synthesize("float32", 4, 0, 10, 12, 16, 1, 1, 1, stencil_shape="diffusion"))
+    dump("synth_hotspot3d_12x12x16_4st", syn.synthesize("float32", 4, 0.5, 12, 12, 16, 1, 1, 1, stencil_shape="hotspot"))
+    dump("synth_hotspot2d_48x64_4st_f64", syn.synthesize("float64", 4, 0, 48, 64, 0, 1, 1, 0, stencil_shape="hotspot"))
+    dump("synth_fork_16x12x16_5st", syn.synthesize("float32", 5, 0.3, 16, 12, 16, 1, 1, 1, fork_frequency=0.5,
+                                                  fork_length_left=1, fork_length_right=2))
 
 
 if __name__ == "__main__":
