@@ -91,16 +91,19 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "reasons": sorted(reasons)}
 
 
+VARIANT = None          # --variant: secondary form of a config (programs.VARIANTS)
+
+
 def build_config(index, scale_i=1):
     from stencilflow_b200 import programs
-    name, prog, halo = programs.baseline_config(index)
+    name, prog, halo = programs.baseline_config(index, VARIANT)
     if scale_i > 1:
         prog["dimensions"][0] *= scale_i
         name += "_x{}".format(scale_i)
     return name, prog, halo
 
 
-INPUT_RANGES = {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)}   # hdiff; everything else U[0,1)
+INPUT_RANGES = {"inp": (1.0, 2.0), "coeff": (0.0, 0.05), "w": (0.9, 1.1)}   # hdiff; everything else U[0,1)
 
 
 def fill_inputs(program, seed=1234, index_offsets=None):
@@ -126,17 +129,16 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
     from stencilflow_b200 import programs, synthetic
     cores = threads or os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    name, prog, _ = programs.baseline_config(index)
+    name, prog, _ = programs.baseline_config(index, VARIANT)
     full = list(prog["dimensions"])
     nops = len(prog["program"])
 
+    short = [d < 256 for d in full]                    # hdiff's vertical axis is kept as it is
+
     def sized(frac):
-        dims = list(full)
-        if len(dims) == 3 and dims[2] < 256:          # hdiff: keep the short vertical axis
-            dims = [max(16, int(dims[0] * frac)), max(16, int(dims[1] * frac)), dims[2]]
-        else:
-            dims = [max(16, int(d * frac) // 8 * 8) for d in dims]
-        return dims
+        return [d if sh else max(16, int(d * frac) // 8 * 8) for d, sh in zip(full, short)]
+
+    iters = ["i", "j", "k"][3 - len(full):]
 
     def run(dims):
         p = json.loads(json.dumps(prog))
@@ -145,7 +147,8 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
         inputs = {}
         for k, (iname, cfg) in enumerate(p["inputs"].items()):
             lo, hi = INPUT_RANGES.get(iname, (0.0, 1.0))
-            inputs[iname] = synthetic.fill_hash(tuple(dims), np.dtype(cfg["data_type"]), 1234 + k, lo, hi)
+            shape = tuple(n for it, n in zip(iters, dims) if it in cfg.get("input_dims", iters))
+            inputs[iname] = synthetic.fill_hash(shape, np.dtype(cfg["data_type"]), 1234 + k, lo, hi)
         ref.allocate_transients()
         ref(**inputs)                                   # warm (page faults, OpenMP team)
         t0 = time.perf_counter()
@@ -164,7 +167,7 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
     itemsize = np.dtype(next(iter(prog["inputs"].values()))["data_type"]).itemsize
     mem_cells = 0.5 * avail / ((nops + 2) * itemsize)
     want_cells = min(cells_full, rate * target_seconds / nops, mem_cells)
-    frac = (want_cells / cells_full) ** (1.0 / (len(full) if not (len(full) == 3 and full[2] < 256) else 2))
+    frac = (want_cells / cells_full) ** (1.0 / max(1, short.count(False)))
     dims = sized(min(1.0, frac))
     if np.prod(dims) > np.prod(probe_dims):
         rate, dt = run(dims)
@@ -209,7 +212,8 @@ def workload_name(index, prog):
     nops = len(prog["program"])
     dt = next(iter(prog["program"].values()))["data_type"]
     kinds = {0: "Jacobi-3D chain", 1: "Jacobi-3D chain", 2: "COSMO hdiff", 3: "Jacobi-2D chain", 4: "Jacobi-3D chain"}
-    return "{} {} {}, {} chained operators (BASELINE.json configs[{}])".format(kinds[index], dims, dt, nops, index)
+    tag = {"jki": ", layout J,K,I", "w1d": ", x 1-D weight w[k] per stage"}.get(VARIANT, "")
+    return "{} {} {}, {} chained operators (BASELINE.json configs[{}]{})".format(kinds[index], dims, dt, nops, index, tag)
 
 
 def main():
@@ -225,9 +229,14 @@ def main():
                     help="N > 1: weak = every rank owns one copy of the config's domain (default for "
                          "configs 1-3); strong = the config's domain is split (default for config 4, "
                          "the 2048^3 x 64 slab-split case of BASELINE.json)")
+    ap.add_argument("--variant", default=None, choices=["jki", "w1d"],
+                    help="secondary form of a config (SURVEY 8d): jki = config 2 in the reference's COSMO "
+                         "layout J,K,I (1024x80x1024); w1d = config 3 with a 1-D weight w[k] in every stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    global VARIANT
+    VARIANT = args.variant
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.scaling is None:
         args.scaling = "strong" if args.config == 4 else "weak"

@@ -228,6 +228,13 @@ class GroupAnalysis:
             raise NotStreamable("only float32/float64 fields stream")
         self.fields: Dict[str, _FieldInfo] = collections.OrderedDict()
         self.taps: Dict[str, List[Tuple[str, int, int, int]]] = {}
+        # lower-dimensional array inputs (``input_dims`` a strict subset of the iterators,
+        # ``kernel_chain_graph.py:382-389``): not streamed -- read straight from global memory
+        # (L1/L2-resident), once per kernel when they do not vary along the streamed dimension
+        self.aux = collections.OrderedDict()                 # name -> Field
+        self.aux_taps: Dict[str, List[Tuple[str, tuple]]] = {}
+        self.aux_reach: Dict[str, List[int]] = {}            # name -> [back, fwd] along the streamed dim
+        self.aux_bc: Dict[str, float] = {}
         produced = {op.name for op in ops}
         later = set()
         seen_group = False
@@ -248,7 +255,16 @@ class GroupAnalysis:
                 if f.data_type != self.dtype:
                     raise NotStreamable("field {} has a different type".format(field))
                 if list(f.dims) != list(program.iterators):
-                    raise NotStreamable("lower-dimensional array input {}".format(field))
+                    bc = op.boundary_conditions.get(field)
+                    if f.kind != "input" or (bc is not None and bc["btype"] == "copy"):
+                        raise NotStreamable("lower-dimensional field {} cannot be read directly".format(field))
+                    self.aux[field] = f
+                    self.aux_taps.setdefault(op.name, []).extend((field, off) for off in op.offsets3(field))
+                    if bc is not None:
+                        val = float(bc["value"]) if bc["btype"] == "constant" else float(JUNK_VAL)
+                        if self.aux_bc.setdefault(field, val) != val:
+                            raise NotStreamable("consumers of {} disagree on the boundary value".format(field))
+                    continue
                 if field not in self.fields:
                     if field in produced:
                         raise NotStreamable("operators out of order")
@@ -281,8 +297,32 @@ class GroupAnalysis:
             info = self.fields[op.name]
             if not info.stored and not info.consumed:
                 raise NotStreamable("dead operator {}".format(op.name))
+        if not any(i.kind == "ext" for i in self.fields.values()):
+            raise NotStreamable("group reads no full-dimensional field")
         self._lags()
         self._halos()
+        spos = 3 - self.ndim                      # position of the streamed iterator in (i, j, k)
+        for op in ops:
+            for (field, off) in self.aux_taps.get(op.name, []):
+                if off[spos] is not None:
+                    r = self.aux_reach.setdefault(field, [0, 0])
+                    r[0] = max(r[0], self.fields[op.name].back + max(0, -off[spos]))
+                    r[1] = max(r[1], self.fields[op.name].fwd + max(0, off[spos]))
+
+    def aux_split(self, off):
+        """(d_stream, d_row, d_col) of a lower-dimensional tap, None for dimensions the field lacks."""
+        if self.ndim == 3:
+            return off[0], off[1], off[2]
+        return off[1], None, off[2]
+
+    def aux_hoisted(self):
+        """Distinct (field, offsets) taps that do not vary along the streamed dimension."""
+        out = []
+        for op in self.ops:
+            for (field, off) in self.aux_taps.get(op.name, []):
+                if self.aux_split(off)[0] is None and (field, off) not in out:
+                    out.append((field, off))
+        return out
 
     def _is_exchange(self, dj, dk):
         return dj != 0 or (self.exchange_cols and dk != 0)
@@ -366,7 +406,20 @@ class GroupAnalysis:
         fitted to ptxas' allocations of the Jacobi/hdiff kernels (spill-free iff estimate <= limit)."""
         per = self.dtype.bytes // 4
         live = sum(max(1, i.window - 1) for i in self.fields.values() if i.consumed)
-        return (live + 2) * R * V * per + 8 + min(12, R * V * per) * len(self.ops)
+        hoisted = 0
+        for (field, off) in self.aux_hoisted():
+            _, dr, dc = self.aux_split(off)
+            hoisted += (R if dr is not None else 1) * (V if dc is not None else 1) * per
+        per_step = 0                  # taps loaded per plane: live only while their operator is evaluated
+        for op in self.ops:
+            n = 0
+            for (field, off) in self.aux_taps.get(op.name, []):
+                ds, dr, dc = self.aux_split(off)
+                if ds is not None:
+                    n += (R if dr is not None else 1) * (V if dc is not None else 1) * per
+            per_step = max(per_step, n)
+        hoisted += per_step
+        return (live + 2) * R * V * per + 8 + min(12, R * V * per) * len(self.ops) + hoisted
 
 
 class Geometry:
@@ -573,6 +626,8 @@ class StreamKernelGen:
         stored = [i for i in a.fields.values() if i.stored]
         params = ["const __grid_constant__ CUtensorMap tm_{}".format(n) for n in range(len(ext))]
         params += ["{}* __restrict__ o_{}".format(T, n) for n in range(len(stored))]
+        self.aux_name = {name: "x_{}".format(n) for n, name in enumerate(a.aux)}
+        params += ["const {}* __restrict__ {}".format(T, self.aux_name[name]) for name in a.aux]
         self.sc_name = {s: "s{}".format(n) for n, s in enumerate(self.scalars)}
         params += ["const {} {}".format(ctype_of(self.program.fields[s].data_type), self.sc_name[s])
                    for s in self.scalars]
@@ -658,6 +713,10 @@ class StreamKernelGen:
                 e("int xr_{} = 0;".format(self.fid[i.name]))
             if i.col_ring and not self.static(i.col_ring):
                 e("int xc_{} = 0;".format(self.fid[i.name]))
+        # lower-dimensional inputs that do not vary along the streamed dimension: loaded once
+        self.aux_regs = {}
+        for n, (field, off) in enumerate(a.aux_hoisted()):
+            self.aux_regs[(field, off)] = self._emit_aux_load(field, off, None, "ax{}".format(n), 1)
         tile_bytes = g.TR * g.TC * self.ct.bytes
         e("const int t_end = c_end + ({});".format(a.t_end_offset()))
         if U > 1:
@@ -755,6 +814,7 @@ class StreamKernelGen:
             g.NT, name, ", ".join(params), body))
         args = [("tmap", {"field": i.name, "box": self._box()}) for i in ext]
         args += [("buf", i.name) for i in stored]
+        args += [("buf", name) for name in a.aux]
         args += [("scalar", self.program.fields[s].data_type, s) for s in self.scalars]
         args += [("slab",), ("chunk",)]
         return name, src, args
@@ -872,6 +932,73 @@ class StreamKernelGen:
                     e("sf_sts_if(lane == 31, {base} + {o}, {c});".format(
                         base=base, o=(R + r) * n + q, c=self.cellref("nv[{}]".format(r), V - n + q)), 2)
 
+    # ------------------------------------------------------------------ lower-dimensional inputs
+    def _aux_bc(self, field):
+        """Value an out-of-domain tap of ``field`` reads (``cpu.py:73-102``), or None if no tap can."""
+        return self.ana.aux_bc.get(field)
+
+    def _emit_aux_load(self, field, off, plane, name, indent, bc=None):
+        """Declares ``name`` and loads into it what one tap of a lower-dimensional input reads for the
+        thread's cells: ``name[rows][V/G]`` (packed like every other value) when the field varies along
+        k, ``name[rows]`` otherwise; rows = R if it varies along the row dimension, else 1.  Indices are
+        clamped into the (slab-local) array, positions outside the domain read the boundary value.
+        Returns (name, has_row, has_col)."""
+        a, g, e, T = self.ana, self.geo, self.emit, self.T
+        f = a.aux[field]
+        ds, dr, dc = a.aux_split(off)
+        it_s, it_r = self.program.iterators[0], ("j" if a.ndim == 3 else None)
+        ext = self.program.extents
+        strides, stride = {}, 1
+        for d in reversed(f.dims):
+            strides[d] = stride
+            stride *= ext[d]
+        has_r, has_c = dr is not None, dc is not None
+        RR = g.R if has_r else 1
+        bcv = bc if bc is not None else self._aux_bc(field)
+        px = self.aux_name[field]
+        if has_c:
+            e("{ET} {n}[{RR}][{VH}];".format(ET=self.ET, n=name, RR=RR, VH=self.VH), indent)
+        else:
+            e("{T} {n}[{RR}];".format(T=T, n=name, RR=RR), indent)
+        fwd = max([i.fwd for i in a.ext_fields] + [r[1] for r in a.aux_reach.values()])
+        for r in range(RR):
+            for v in range(g.V if has_c else 1):
+                terms, conds = [], []
+                if ds is not None:
+                    pos = "({} + ({}))".format(plane, ds)
+                    hi = "min({}, s_end + {}) - 1".format(self.NS, fwd)
+                    terms.append("(i64)(min(max({p}, s_base), {hi}) - s_base) * {st}".format(p=pos, hi=hi, st=strides[it_s]))
+                    if ds:
+                        conds.append("(unsigned){} < {}u".format(pos, self.NS))
+                if has_r:
+                    pos = "(gj0 + ({}))".format(r + dr)
+                    terms.append("(i64)min(max({p}, 0), {n}) * {st}".format(p=pos, n=self.NJ - 1, st=strides[it_r]))
+                    if dr:
+                        conds.append("(unsigned){} < {}u".format(pos, self.NJ))
+                if has_c:
+                    pos = "(gk + ({}))".format(v + dc)
+                    terms.append("(i64)min(max({p}, 0), {n}) * {st}".format(p=pos, n=self.NK - 1, st=strides["k"]))
+                    if dc:
+                        conds.append("(unsigned){} < {}u".format(pos, self.NK))
+                load = "__ldg({} + ({}))".format(px, " + ".join(terms))
+                if conds:
+                    load = "(({}) ? {} : {})".format(" && ".join(conds), load, self.lit(bcv if bcv is not None else 0.0))
+                dst = "{}[{}]".format(name, r)
+                if has_c:
+                    dst = self.cellref(dst, v)
+                e("{} = {};".format(dst, load), indent)
+        return name, has_r, has_c
+
+    def _aux_key(self, t: ex.Tap):
+        dims = self.ana.aux[t.field].dims
+        return (t.field, tuple(o if it in dims else None for it, o in zip(ex.ITERATORS, t.offset)))
+
+    def _aux_value(self, regs, r, v):
+        """C expression of cell v of row r of a loaded lower-dimensional tap (scalar form)."""
+        name, has_r, has_c = regs
+        row = "{}[{}]".format(name, r if has_r else 0)
+        return self.cellref(row, v) if has_c else row
+
     def _produce_ext(self, info: _FieldInfo, u: int):
         g, e = self.geo, self.emit
         f = self.fid[info.name]
@@ -984,6 +1111,15 @@ class StreamKernelGen:
                 return "l_{}[{}]".format(tag, nl + c)
             return "g_{}[{}]".format(tag, c - V)
 
+        # lower-dimensional inputs: taps that vary along the streamed dimension are loaded per plane
+        self.aux_cur = {}
+        for n, (field, off) in enumerate(a.aux_taps.get(op.name, [])):
+            if (field, off) in self.aux_cur:
+                continue
+            if (field, off) in self.aux_regs:
+                self.aux_cur[(field, off)] = self.aux_regs[(field, off)]
+            else:
+                self.aux_cur[(field, off)] = self._emit_aux_load(field, off, "(" + plane + ")", "ay{}".format(n), 3)
         self._open_plane(info, u)
         if self.G == 1:
             self._emit_scalar_cells(op, tap_key, tap_cell)
@@ -1011,7 +1147,8 @@ class StreamKernelGen:
                 for s in op.statements:
                     rhs = ex.emit_c(
                         s.value,
-                        tap=lambda t, r=r, v=v: tap_cell(t, r, v + tap_key(t, r)[1]),
+                        tap=lambda t, r=r, v=v: (self._aux_value(self.aux_cur[self._aux_key(t)], r, v)
+                                                 if t.field in self.ana.aux else tap_cell(t, r, v + tap_key(t, r)[1])),
                         var=lambda n, local=local: self._var(n, local, op),
                         literal=self.lit,
                         call=lambda fn, args: "{}({})".format(math_fn[fn], ", ".join(args)))
@@ -1078,6 +1215,10 @@ class StreamKernelGen:
                         if x.name in local:
                             return local[x.name]
                         return ("c", self._var(x.name, {}, op))
+                    if isinstance(x, ex.Tap) and x.field in self.ana.aux:
+                        name, has_r, has_c = self.aux_cur[self._aux_key(x)]
+                        row = "{}[{}]".format(name, r if has_r else 0)
+                        return ("p", "{}[{}]".format(row, h)) if has_c else ("c", row)
                     if isinstance(x, ex.Tap):
                         key, dk = tap_key(x, r)
                         vec, tag = names[key]
@@ -1265,8 +1406,8 @@ def candidate_geometries(program, ops, options):
     nk = program.shape[-1]
     out = []
     if ndim == 3:
-        rows = [options.rows_per_thread] if options.rows_per_thread else [4, 3, 2, 1]
-        warps = [options.warps] if options.warps else [16, 12, 8]
+        rows = [options.rows_per_thread] if options.rows_per_thread else [4, 5, 3, 2, 1]
+        warps = [options.warps] if options.warps else [16, 12, 10, 8]
         for R in rows:
             for w in warps:
                 out.append((R, w, 1, 32))
@@ -1298,7 +1439,7 @@ def candidate_geometries(program, ops, options):
 # windows do not fit the register file of the chosen CTA size.
 HBM_BYTES_PER_S = 6.1e12
 UPDATES_PER_S = {4: 2.7e12, 8: 0.95e12}     # computed cell updates per second at R = 4, by element size
-ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0}
+ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0, 5: 1.0}
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
 
 
@@ -1313,7 +1454,12 @@ def modelled_time(program, ops, ana, geo):
     nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields)
     nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
     eff = _tile_efficiency(ana, geo)
-    used = min(1.0, program.shape[-1] / float(geo.BK))
+    # tiles that stick out of the domain compute cells nobody stores (80 rows under 32-row tiles = 3 tiles)
+    nk = program.shape[-1]
+    used = nk / float(-(-nk // geo.BK) * geo.BK)
+    if ana.ndim == 3:
+        nj = program.shape[-2]
+        used *= nj / float(-(-nj // geo.BJ) * geo.BJ)
     t_mem = nbytes / HBM_BYTES_PER_S
     rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), UPDATES_PER_S[ana.dtype.bytes]))
     rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else 1.0
@@ -1324,31 +1470,40 @@ def modelled_time(program, ops, ana, geo):
 def choose_geometry(program, ops, options):
     """Pick (V, R, warps, prefetch) for a candidate group -- the admissible geometry with the lowest
     modelled pass time -- or return None when the group cannot stream."""
-    try:
-        V, candidates = candidate_geometries(program, ops, options)
-        if V is None:
-            raise NotStreamable("innermost extent not a multiple of the vector width")
-        prefetch = options.prefetch or 2
-        best = None
-        explicit = bool(options.rows_per_thread and options.warps)
-        for (R, WR, WC, KS) in candidates:
-            try:
-                ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(options, "sync", "") or DEFAULT_SYNC)
-            except NotStreamable:
+    import copy
+    trials = [options]
+    if len(program.shape) == 2 and not getattr(options, "vector", 0):
+        # 2-D rows: 32 bytes per thread first (half the shuffles and ring words per cell; measured
+        # 1.27x faster than 16 bytes on the float64 chain, profiles/r01_sweep_sync_prefetch.txt)
+        wide = copy.copy(options)
+        wide.vector = 32 // ops[0].data_type.bytes
+        trials = [wide, options]
+    best = None
+    for opts in trials:
+        try:
+            V, candidates = candidate_geometries(program, ops, opts)
+            if V is None:
                 continue
-            if geo.smem > SMEM_LIMIT:
-                continue
-            if not explicit and ana.register_estimate(R, V) > register_limit(geo.NT) + REG_SLACK:
-                continue
-            t = modelled_time(program, ops, ana, geo)
-            if best is None or t < best[0] * (1 - 1e-6):
-                best = (t, ana, geo)
-        if best is None:
-            return None
-        return best[1], best[2]
-    except NotStreamable:
+            prefetch = opts.prefetch or 2
+            explicit = bool(opts.rows_per_thread and opts.warps)
+            for (R, WR, WC, KS) in candidates:
+                try:
+                    ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
+                    geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(opts, "sync", "") or DEFAULT_SYNC)
+                except NotStreamable:
+                    continue
+                if geo.smem > SMEM_LIMIT:
+                    continue
+                if not explicit and ana.register_estimate(R, V) > register_limit(geo.NT) + REG_SLACK:
+                    continue
+                t = modelled_time(program, ops, ana, geo)
+                if best is None or t < best[0] * (1 - 1e-6):
+                    best = (t, ana, geo)
+        except NotStreamable:
+            continue
+    if best is None:
         return None
+    return best[1], best[2]
 
 
 def group_cost(program, ops, options):
@@ -1478,7 +1633,9 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
         return (gx, gy, max(1, -(-(e_ - b) // ci)))
 
     stored = [i.name for i in ana.fields.values() if i.stored]
-    reads = [i.name for i in ana.ext_fields]
+    reads = [i.name for i in ana.ext_fields] + list(ana.aux)
+    reach = {i.name: (i.back, i.fwd) for i in ana.ext_fields}
+    reach.update({name: tuple(r) for name, r in ana.aux_reach.items()})
     launch = LaunchSpec(kernel=name, grid_fn=grid, block=(geo.NT, 1, 1), smem=geo.smem, args=args,
                         ops=[op.name for op in ops], reads=reads, writes=stored,
                         cells_per_unit=program.cells * len(ops), family="streamed",
@@ -1491,7 +1648,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                               "register_estimate": ana.register_estimate(geo.R, geo.V),
                               "stream_overhead_planes": overhead,
                               "back": max(i.back for i in ana.fields.values()),
-                              "reach": {i.name: (i.back, i.fwd) for i in ana.ext_fields},
+                              "reach": reach,
                               "tile_efficiency": _tile_efficiency(ana, geo),
                               "fwd": ana.max_lag,
                               "chunk_fn": chunk_for})

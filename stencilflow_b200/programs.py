@@ -61,6 +61,29 @@ def hdiff(shape, dtype="float32"):
         }}
 
 
+def hdiff_jki(shape, dtype="float32"):
+    """The same program in the reference's own COSMO layout convention J,K,I
+    (``stencilflow/sdfg_to_stencilflow.py:46-68``): ``shape = [NJ, NK, NI]``, the horizontal plane is
+    (iterator i, iterator k), the vertical axis (iterator j) carries no taps (SURVEY section 8d,
+    config 3 "run that variant too")."""
+    sh = {"type": "shrink"}
+    return {
+        "inputs": {"inp": {"data": "constant:1.0", "data_type": dtype},
+                   "coeff": {"data": "constant:0.025", "data_type": dtype}},
+        "outputs": ["out"], "dimensions": list(shape),
+        "program": {
+            "lap": {"computation_string": "lap = 4.0*inp[i,j,k] - (inp[i,j,k+1] + inp[i,j,k-1] + inp[i+1,j,k] + inp[i-1,j,k])",
+                    "boundary_conditions": {"inp": dict(sh)}, "data_type": dtype},
+            "flx": {"computation_string": "d = lap[i,j,k+1] - lap[i,j,k]; flx = 0.0 if d*(inp[i,j,k+1] - inp[i,j,k]) > 0.0 else d",
+                    "boundary_conditions": {"lap": dict(sh), "inp": dict(sh)}, "data_type": dtype},
+            "fly": {"computation_string": "d = lap[i+1,j,k] - lap[i,j,k]; fly = 0.0 if d*(inp[i+1,j,k] - inp[i,j,k]) > 0.0 else d",
+                    "boundary_conditions": {"lap": dict(sh), "inp": dict(sh)}, "data_type": dtype},
+            "out": {"computation_string": "out = inp[i,j,k] - coeff[i,j,k]*(flx[i,j,k] - flx[i,j,k-1] + fly[i,j,k] - fly[i-1,j,k])",
+                    "boundary_conditions": {"inp": dict(sh), "coeff": dict(sh), "flx": dict(sh), "fly": dict(sh)},
+                    "data_type": dtype},
+        }}
+
+
 def programs_dir():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     d = os.environ.get("SFB200_PROGRAMS", os.path.join(root, "programs"))
@@ -77,8 +100,30 @@ def write_program(prog, name, directory=None):
     return path
 
 
-def baseline_config(index):
-    """(name, program dict, halo) for configs[index] of BASELINE.json."""
+def jacobi2d_weighted(shape, steps, dtype="float64", boundary=None):
+    """BASELINE configs[3], secondary variant: the 2-D chain with every stage
+    multiplied by a 1-D weight ``w[k]`` (``input_dims ["k"]``) -- a lower-dimensional input inside a
+    fused chain.  The reference front end cannot express this in a 2-D program (its ``"[" -> "[i,"``
+    rewrite, ``kernel_chain_graph.py:399-403``); semantics by analogy with the 3-D case."""
+    prog = jacobi2d_chain(shape, steps, dtype=dtype, boundary=boundary)
+    prog["inputs"]["w"] = {"data": "constant:1.0", "data_type": dtype, "input_dims": ["k"]}
+    for op in prog["program"].values():
+        op["computation_string"] = op["computation_string"].replace("0.25 *", "0.25 * w[k] *")
+    return prog
+
+
+VARIANTS = {2: ("jki",), 3: ("w1d",)}
+
+
+def baseline_config(index, variant=None):
+    """(name, program dict, halo) for configs[index] of BASELINE.json (``variant``: the secondary
+    forms SURVEY section 8d asks to report alongside: "jki" for config 2, "w1d" for config 3)."""
+    if variant and variant not in VARIANTS.get(index, ()):
+        raise ValueError("config {} has no variant {!r}".format(index, variant))
+    if index == 2 and variant == "jki":
+        return "hdiff_jki_1024x80x1024_f32", hdiff_jki([1024, 80, 1024]), 2
+    if index == 3 and variant == "w1d":
+        return "jacobi2d_32768_16itr_f64_shrink_w1d", jacobi2d_weighted([32768, 32768], 16), 16
     if index == 0:
         return "jacobi3d_32x32x32_8itr_8vec", jacobi3d_chain([32, 32, 32], 8, vectorization=4), 0
     if index == 1:

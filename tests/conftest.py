@@ -39,6 +39,8 @@ HALO = {
     "hdiff_16x20x8_f64": 2,
     "jacobi2d_96x128_6itr_shrink_f64": 6,
     "jacobi3d_24x20x40_4itr_shrink_f64": 4,
+    "lowdim3d_20x24x48_3st_shrink_f64": 4,
+    "jacobi2d_96x128_6itr_w1d_shrink_f64": 6,
 }
 
 # value ranges of the random test inputs; hdiff subtracts a small correction from `inp`, so its

@@ -137,6 +137,49 @@ def main():
             "b": {"computation_string": "b = w[k] * (a[j-1,k] + a[j+1,k]) + w[k+1] * h[j] * a[j,k-1]",
                   "boundary_conditions": {"a": {"type": "constant", "value": 3.0}, "w": {"type": "constant", "value": 0.0},
                                           "h": {"type": "constant", "value": 0.0}}, "data_type": "float64"}}})
+    # lower-dimensional inputs inside fusable chains (every subset of the iterators, with offsets):
+    # the streamed kernels read them straight from global memory
+    c1 = {"type": "constant", "value": 1.0}
+    sh = {"type": "shrink"}
+    low = {
+        "inputs": {"a": {"data": "constant:1.0", "data_type": "float32"},
+                   "wk": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["k"]},
+                   "wj": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["j"]},
+                   "wi": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["i"]},
+                   "pjk": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["j", "k"]},
+                   "pik": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["i", "k"]},
+                   "pij": {"data": "constant:0.5", "data_type": "float32", "input_dims": ["i", "j"]}},
+        "outputs": ["b2"], "dimensions": [20, 24, 48],
+        "program": {
+            "b0": {"computation_string": "b0 = 0.2*wk[k]*(a[i-1,j,k] + a[i+1,j,k] + a[i,j-1,k] + a[i,j+1,k]) + "
+                                         "wj[j+1]*a[i,j,k-1] + wi[i-1]*a[i,j,k+1] + pjk[j,k+1]",
+                   "boundary_conditions": {"a": c1, "wk": c1, "wj": c1, "wi": c1, "pjk": c1}, "data_type": "float32"},
+            "b1": {"computation_string": "b1 = 0.25*(b0[i-1,j,k] + b0[i+1,j,k] + b0[i,j-1,k] + b0[i,j,k+1]) * "
+                                         "pik[i+1,k-1] + pij[i,j] - wk[k-3]",
+                   "boundary_conditions": {"b0": c1, "pik": c1, "pij": c1, "wk": c1}, "data_type": "float32"},
+            "b2": {"computation_string": "b2 = (b1[i,j,k] + b1[i,j+1,k] + b1[i,j,k-1]) * pij[i-1,j+1] + pjk[j-1,k] * wi[i]",
+                   "boundary_conditions": {"b1": c1, "pij": c1, "pjk": c1, "wi": c1}, "data_type": "float32"}}}
+    dump("lowdim3d_20x24x48_3st_f32", low)
+    low64 = json.loads(json.dumps(low).replace("float32", "float64"))
+    for op in low64["program"].values():
+        op["boundary_conditions"] = {k: dict(sh) for k in op["boundary_conditions"]}
+    dump("lowdim3d_20x24x48_3st_shrink_f64", low64)
+    # BASELINE configs[3], secondary variant: the 2-D chain multiplied by 1-D weights
+    for name, shape, dtype, bc in (("jacobi2d_96x128_6itr_w1d_shrink_f64", [96, 128], "float64", sh),
+                                   ("jacobi2d_64x256_6itr_w1d_const_f32", [64, 256], "float32",
+                                    {"type": "constant", "value": 0.5})):
+        p2 = jacobi2d(shape[0], shape[1], 6, dtype=dtype, bc=bc)
+        p2["inputs"]["w"] = {"data": "constant:0.9", "data_type": dtype, "input_dims": ["k"]}
+        p2["inputs"]["u"] = {"data": "constant:1.1", "data_type": dtype, "input_dims": ["j"]}
+        for n, op in enumerate(p2["program"].values()):
+            if n % 2 == 0:
+                op["computation_string"] = op["computation_string"].replace("0.25 *", "0.25 * w[k] *")
+                op["boundary_conditions"]["w"] = dict(bc)
+            else:
+                op["computation_string"] = op["computation_string"].replace("0.25 *", "0.25 * w[k+1] * u[j-1] *")
+                op["boundary_conditions"]["w"] = dict(bc)
+                op["boundary_conditions"]["u"] = dict(bc)
+        dump(name, p2)
     dump("fork_join_20x16x24", {
         "inputs": {"a": {"data": "constant:1.0", "data_type": "float32"}},
         "outputs": ["e", "c"], "dimensions": [20, 16, 24],

@@ -46,6 +46,8 @@ def _run_world(path, fuse, world=2, seed=5):
     ("hdiff_24x28x16", True),
     ("fork_join_20x16x24", False),
     ("box3d_10x12x16", False),
+    ("lowdim3d_20x24x48_3st_f32", True),
+    ("ref_varying_dimensionality", True),
 ])
 def test_two_ranks_reproduce_single_domain(native_lib, name, fuse):
     results = _run_world(program_path(name), fuse)

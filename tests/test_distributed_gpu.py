@@ -26,6 +26,8 @@ def _gpu_count(native_lib):
     ("jacobi2d_96x128_6itr_shrink_f64", True),
     ("hdiff_24x28x16", True),
     ("fork_join_20x16x24", True),
+    ("lowdim3d_20x24x48_3st_f32", True),
+    ("ref_varying_dimensionality", True),
 ])
 def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if _gpu_count(native_lib) < 2:
