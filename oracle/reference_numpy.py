@@ -28,9 +28,18 @@ What is restated, with the reference lines followed:
 
 PARITY PINNING: the reference stores no output vectors for this path (its program tests compare
 FPGA emulation with the CPU SDFG generated from the same JSON, ``test/test_stencilflow.py:188-224``)
-and cannot be imported under Python 3.12 (DaCe 0.10.8 needs <3.10).  This oracle is pinned by
-(1) hand-derived known answers for every program of ``test/stencils`` (``tests/golden/``),
-(2) agreement with the independently generated C++/OpenMP restatement in ``reference_cpp.py``.
+and its compiled paths cannot run under Python 3.12 (DaCe 0.10.8 needs <3.10).  This oracle is pinned by
+(1) OUTPUTS OF THE REFERENCE ITSELF: its pure-Python dataflow simulator (``stencilflow/simulator.py``,
+    ``kernel.py:634-738``, ``calculator.py``) does run here, unmodified, behind a stub for the DaCe type
+    names; ``tests/golden/make_reference_sim_golden.py`` ran it on 10 program/input cases inside the
+    simulator's envelope (3-D, constant boundaries, full-dimensional inputs) and
+    ``tests/test_oracle.py::test_oracles_match_reference_simulator`` requires this module to reproduce
+    the stored outputs (max relative error 2e-6 float32 / 1e-13 float64);
+(2) hand-derived known answers for every program of ``test/stencils`` (``tests/golden/known_answers.json``),
+    which also cover what the simulator cannot run (2-D programs, lower-dimensional and 0-D inputs);
+(3) agreement with the independently generated C++/OpenMP restatement in ``reference_cpp.py``.
+``shrink`` and ``copy`` boundaries have no executable reference here (the simulator raises
+NotImplementedError for them, ``kernel.py:534-540``): for those the pinning is (2)+(3) only.
 """
 
 import ast

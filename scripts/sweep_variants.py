@@ -4,8 +4,9 @@ produces bit-identical output (on-device checksum of the program outputs against
 
     python scripts/sweep_variants.py --config 1 d4r4w8 d4r4w8p5 d4r4w8p5s ...
 
-A variant is written d<depth>[r<rows>][v<cells>][w<warps>][k<threads per row>][p<prefetch>][s]
-where a trailing ``s`` selects neighbour-only ("pair") synchronisation.
+A variant is written d<depth>[r<rows>][v<cells>][w<warps>][k<threads per row>][p<prefetch>][s][x]
+where a trailing ``s`` selects neighbour-only ("pair") synchronisation and ``x`` direct reads of the
+input's neighbour rows from the TMA ring.
 """
 import argparse
 import os
@@ -23,13 +24,13 @@ from stencilflow_b200.cuda_program import CudaProgram  # noqa: E402
 
 
 def parse(text):
-    m = re.fullmatch(r"d(\d+)(?:r(\d+))?(?:v(\d+))?(?:w(\d+))?(?:k(\d+))?(?:p(\d+))?(s?)", text)
+    m = re.fullmatch(r"d(\d+)(?:r(\d+))?(?:v(\d+))?(?:w(\d+))?(?:k(\d+))?(?:p(\d+))?(s?)(x?)", text)
     if not m:
         raise SystemExit("bad variant " + text)
-    d, r, v, w, k, p, s = m.groups()
+    d, r, v, w, k, p, s, x = m.groups()
     return planner.PlanOptions(max_depth=int(d), rows_per_thread=int(r or 0), vector=int(v or 0),
                                warps=int(w or 0), threads_per_row=int(k or 0), prefetch=int(p or 0),
-                               sync="pair" if s else "cta")
+                               sync="pair" if s else "cta", direct=1 if x else 0)
 
 
 def main():

@@ -31,6 +31,10 @@ def main():
     for name, v in itertools.product([n for n in names3 if n != "hdiff_24x28x16"], T.PAIR_VARIANTS_3D):
         jobs.append((program_path(name), PlanOptions(max_depth=v[0], rows_per_thread=v[1], warps=v[2],
                                                      threads_per_row=v[3], prefetch=v[4], sync=v[5])))
+    for name, v in itertools.product(["ref_jacobi3d_32x32x32_8itr_8vec", "fork_join_20x16x24", "box3d_10x12x16",
+                                      "jacobi3d_16x24x32_5itr_const1"], T.DIRECT_VARIANTS_3D):
+        jobs.append((program_path(name), PlanOptions(max_depth=v[0], rows_per_thread=v[1], warps=v[2],
+                                                     threads_per_row=v[3], prefetch=v[4], direct=1)))
     names2 = ["jacobi2d_96x128_6itr_shrink_f64", "jacobi2d_64x64_4itr_const_f32", "ref_jacobi2d_128x128"]
     for name, v in itertools.product(names2, [(1, 8, 0), (2, 8, 0), (4, 8, 0), (6, 16, 0), (4, 8, 4), (2, 16, 8), (3, 8, 8)]):
         jobs.append((program_path(name), PlanOptions(max_depth=v[0], warps=v[1], vector=v[2])))

@@ -423,7 +423,7 @@ class GroupAnalysis:
 
 
 class Geometry:
-    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32, sync="cta"):
+    def __init__(self, ana: GroupAnalysis, V, R, WR, WC, prefetch, KS=32, sync="cta", direct=False):
         """``KS`` = threads per tile row.  32 (a warp per row, k-neighbours by shuffle) in general;
         for groups without k-taps on a narrow innermost dimension the whole extent is one row of
         ``KS = NK / V`` threads and thread t owns row group t / KS ("flat lanes": no idle lanes)."""
@@ -442,7 +442,19 @@ class Geometry:
         self.BJ = self.TR - self.HJ0 - self.HJ1
         self.BK = self.TC - self.HK0 - self.HK1
         self.P = prefetch
-        self.D = prefetch + 1
+        # "direct" rows: a thread reads the j-neighbour rows of a streamed input straight from the
+        # plane TMA put into shared memory (any thread may read any row of it) instead of from an
+        # exchange ring the owners re-publish them into -- two shared-memory stores per thread and
+        # plane less.  The TMA ring then keeps a plane as long as its rows are read (``keep`` extra
+        # slots).  Only for inputs whose out-of-domain cells need no fix-up (TMA's zero fill is the
+        # boundary value), 3-D tiles, CTA-wide synchronisation.
+        self.direct = {}
+        if direct and ana.ndim == 3 and sync != "pair":
+            for i in ana.ext_fields:
+                if i.row_ring and not i.col_ring and (i.bc is None or float(i.bc) == 0.0):
+                    self.direct[i.name] = i.row_ring - 1
+        self.keep = max(self.direct.values()) if self.direct else 0
+        self.D = prefetch + 1 + self.keep
         if ana.ndim == 2:
             self.BJ = 1
         if self.BJ < 1 or self.BK < V:
@@ -485,7 +497,7 @@ class Geometry:
             off += self.D * self.TR * self.TC * b
             off = (off + 127) & ~127
         for i in ana.fields.values():
-            if i.row_ring:
+            if i.row_ring and i.name not in self.direct:
                 self.xrow_off[i.name] = off
                 off += i.row_ring * self.WR * 2 * i.row_reach * self.TC * b
                 off = (off + 127) & ~127
@@ -548,7 +560,7 @@ class StreamKernelGen:
     def _choose_unroll(self, cap):
         a, g = self.ana, self.geo
         windows = [i.window for i in a.fields.values() if i.consumed and i.window > 1]
-        rings = [i.row_ring for i in a.fields.values() if i.row_ring]
+        rings = [i.row_ring for i in a.fields.values() if i.row_ring and i.name not in g.direct]
         rings += [i.col_ring for i in a.fields.values() if i.col_ring]
         wmax = max(windows + [1])
         for periods in ([g.D] + rings, [g.D], []):
@@ -685,7 +697,7 @@ class StreamKernelGen:
             e("{T}* const tile_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
                 T=T, f=self.fid[i.name], o=g.tile_off[i.name]))
         for i in a.fields.values():
-            if i.row_ring:
+            if i.row_ring and i.name not in g.direct:
                 e("{T}* const xrow_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
                     T=T, f=self.fid[i.name], o=g.xrow_off[i.name]))
             if i.col_ring:
@@ -709,7 +721,7 @@ class StreamKernelGen:
                 e("for (int r = 0; r < {}; ++r)".format(R), 2)
                 e("#pragma unroll", 3)
                 e("for (int v = 0; v < {}; ++v) w_{}[a][r][v] = {};".format(self.VH, self.fid[i.name], zero), 3)
-            if i.row_ring and not self.static(i.row_ring):
+            if i.row_ring and i.name not in g.direct and not self.static(i.row_ring):
                 e("int xr_{} = 0;".format(self.fid[i.name]))
             if i.col_ring and not self.static(i.col_ring):
                 e("int xc_{} = 0;".format(self.fid[i.name]))
@@ -727,6 +739,8 @@ class StreamKernelGen:
         else:
             e("const int t_begin = c_begin + ({});".format(a.t_begin_offset()))
         static_d = self.static(g.D)
+        if g.direct and not static_d:
+            raise NotStreamable("direct input rows need a TMA ring whose depth divides the unroll factor")
         if static_d:
             e("u32 phase = 0;")
         else:
@@ -862,7 +876,7 @@ class StreamKernelGen:
             if not static_d:
                 e("if (++slot == {}) {{ slot = 0; phase ^= 1; }}".format(g.D), 2)
             for i in a.fields.values():
-                if i.row_ring and not self.static(i.row_ring):
+                if i.row_ring and i.name not in g.direct and not self.static(i.row_ring):
                     e("if (++xr_{f} == {n}) xr_{f} = 0;".format(f=self.fid[i.name], n=i.row_ring), 2)
                 if i.col_ring and not self.static(i.col_ring):
                     e("if (++xc_{f} == {n}) xc_{f} = 0;".format(f=self.fid[i.name], n=i.col_ring), 2)
@@ -908,7 +922,7 @@ class StreamKernelGen:
                         b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=self.lit(info.bc)), 4)
             e("}", 3)
             e("}")
-        if info.row_ring:
+        if info.row_ring and info.name not in g.direct:
             n = info.row_reach
             # layout [ring][WR][2][n][TC]
             slot = self.ring_slot("xr_" + f, info.row_ring, 0, u)
@@ -1059,6 +1073,27 @@ class StreamKernelGen:
             else:
                 # a row owned by the neighbouring warp: read it (and its shifted columns) from the ring
                 n = src.row_reach
+                if field in g.direct:
+                    # ... or, for a streamed input, from the plane itself in the TMA ring (rows beyond
+                    # the tile belong to halo cells nobody uses: clamp them into the tile)
+                    slot = (u - age) % g.D
+                    row = "max(r0 - {}, 0)".format(-rr) if rr < 0 else "min(r0 + {}, {})".format(rr, g.TR - 1)
+                    base = "tile_{f} + {slot} * {sz} + {row} * {TC}".format(f=f, slot=slot, sz=g.TR * g.TC,
+                                                                         row=row, TC=g.TC)
+                    e("const {T}* const p_{tag} = {base};".format(T=T, tag=tag, base=base), 3)
+                    e("{ET} x_{tag}[{VH}];".format(ET=self.ET, tag=tag, VH=self.VH), 3)
+                    e(self.ldv("x_" + tag, "p_{} + c0".format(tag)), 3)
+                    names[(field, age, rr)] = ("x_" + tag, tag)
+                    if nl:
+                        e("{T} l_{tag}[{n}];".format(T=T, tag=tag, n=nl), 3)
+                        for q in range(nl):
+                            e("l_{tag}[{q}] = p_{tag}[max(c0 - {nl} + {q}, 0)];".format(tag=tag, q=q, nl=nl), 3)
+                    if nr:
+                        e("{T} g_{tag}[{n}];".format(T=T, tag=tag, n=nr), 3)
+                        for q in range(nr):
+                            e("g_{tag}[{q}] = p_{tag}[min(c0 + {V} + {q}, {last})];".format(
+                                tag=tag, q=q, V=V, last=g.TC - 1), 3)
+                    continue
                 slot = self.ring_slot("xr_" + f, src.row_ring, age, u)
                 if rr < 0:
                     nbr = "max(wr - 1, 0)"
@@ -1489,7 +1524,8 @@ def choose_geometry(program, ops, options):
             for (R, WR, WC, KS) in candidates:
                 try:
                     ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                    geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(opts, "sync", "") or DEFAULT_SYNC)
+                    geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(opts, "sync", "") or DEFAULT_SYNC,
+                                   direct=bool(getattr(opts, "direct", 0)))
                 except NotStreamable:
                     continue
                 if geo.smem > SMEM_LIMIT:
@@ -1642,7 +1678,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                         info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "threads_per_row": geo.KS,
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
-                              "prefetch": geo.P, "sync": "pair" if geo.pair else "cta", "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "prefetch": geo.P, "sync": "pair" if geo.pair else "cta", "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "register_estimate": ana.register_estimate(geo.R, geo.V),

@@ -95,13 +95,13 @@ class PlanOptions:
     measured plans (``tuned_plans.json``) before falling back on the cost model."""
 
     KNOBS = ("SFB200_FUSE", "SFB200_MAX_DEPTH", "SFB200_ROWS", "SFB200_WARPS", "SFB200_CHUNK", "SFB200_PREFETCH",
-             "SFB200_VEC", "SFB200_KS", "SFB200_SYNC")
+             "SFB200_VEC", "SFB200_KS", "SFB200_SYNC", "SFB200_DIRECT")
 
     def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
-                 prefetch=None, vector=None, threads_per_row=None, sync=None):
+                 prefetch=None, vector=None, threads_per_row=None, sync=None, direct=None):
         env = os.environ
         self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector,
-                                                   threads_per_row, sync))
+                                                   threads_per_row, sync, direct))
                            and not any(k in env for k in self.KNOBS) and env.get("SFB200_TUNED", "1") != "0")
         self.vector = int(env.get("SFB200_VEC", "0")) if vector is None else vector
         self.threads_per_row = int(env.get("SFB200_KS", "0")) if threads_per_row is None else threads_per_row
@@ -112,6 +112,9 @@ class PlanOptions:
         self.chunk = int(env.get("SFB200_CHUNK", "0")) if chunk is None else chunk
         self.prefetch = int(env.get("SFB200_PREFETCH", "0")) if prefetch is None else prefetch
         self.sync = env.get("SFB200_SYNC", "") if sync is None else sync
+        # 1: neighbour rows of a streamed *input* field are read straight from its TMA ring (which then
+        # keeps a plane one step longer) instead of being re-published through an exchange ring
+        self.direct = int(env.get("SFB200_DIRECT", "0")) if direct is None else int(direct)
 
     def as_dict(self):
         return {k: v for k, v in self.__dict__.items() if k != "is_default"}

@@ -106,6 +106,34 @@ def main():
                   "boundary_conditions": {"a": {"type": "constant", "value": 2.0}}, "data_type": "float32"},
             "c": {"computation_string": "c = b[i,j,k] + 0.5 * b[i-1,j,k+3]",
                   "boundary_conditions": {"b": {"type": "constant", "value": 1.0}}, "data_type": "float32"}}})
+    # within the envelope of the reference's dataflow simulator (3-D, full-dimensional list inputs,
+    # constant boundaries, no and/or; calculator.py knows sin/cos/tan/sinh/cosh): these two run through
+    # the reference itself, tests/golden/make_reference_sim_golden.py
+    dump("trig3d_8x10x12_f64", {
+        "inputs": {"a": {"data": "constant:0.75", "data_type": "float64"},
+                   "b": {"data": "constant:0.25", "data_type": "float64"}},
+        "outputs": ["v"], "dimensions": [8, 10, 12],
+        "program": {
+            "u": {"computation_string": "u = sin(a[i,j,k]) * b[i-1,j,k+1] + cos(b[i,j+1,k]) / (1.5 + a[i+1,j,k-1])",
+                  "boundary_conditions": {"a": {"type": "constant", "value": 0.25},
+                                          "b": {"type": "constant", "value": 0.5}}, "data_type": "float64"},
+            "v": {"computation_string": "v = u[i,j,k] if u[i,j-1,k] > a[i,j,k] else (u[i,j,k+2] + 0.5 * u[i-2,j,k])",
+                  "boundary_conditions": {"u": {"type": "constant", "value": 1.0},
+                                          "a": {"type": "constant", "value": 0.25}}, "data_type": "float64"}}})
+    dump("diamond3d_12x10x16", {
+        "inputs": {"a": {"data": "constant:1.0", "data_type": "float32"},
+                   "c": {"data": "constant:0.5", "data_type": "float32"}},
+        "outputs": ["e"], "dimensions": [12, 10, 16],
+        "program": {
+            "b": {"computation_string": "b = 0.5 * (a[i-1,j,k] + a[i+1,j,k]) + c[i,j,k]",
+                  "boundary_conditions": {"a": {"type": "constant", "value": 0.0}}, "data_type": "float32"},
+            "l": {"computation_string": "l = 0.5 * (b[i,j-1,k] + b[i,j+1,k])",
+                  "boundary_conditions": {"b": {"type": "constant", "value": 0.0}}, "data_type": "float32"},
+            "r": {"computation_string": "r = 0.25 * (b[i,j,k-1] + b[i,j,k+1]) + a[i,j,k] * c[i,j+1,k]",
+                  "boundary_conditions": {"b": {"type": "constant", "value": 0.0},
+                                          "c": {"type": "constant", "value": 2.0}}, "data_type": "float32"},
+            "e": {"computation_string": "e = l[i,j,k] + r[i+1,j,k] + 0.5 * r[i-1,j,k]",
+                  "boundary_conditions": {"r": {"type": "constant", "value": 0.0}}, "data_type": "float32"}}})
     dump("math_ops_8x8x8", {
         "inputs": {"a": {"data": "constant:0.75", "data_type": "float32"},
                    "b": {"data": "constant:0.25", "data_type": "float32"},

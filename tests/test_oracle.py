@@ -1,6 +1,7 @@
-"""The oracle against everything that pins it: frozen known answers for the reference's test
-programs (tests/golden/known_answers.json, partly hand-derived), the independent C++/OpenMP
-restatement, and analytic invariants."""
+"""The oracle against everything that pins it: OUTPUTS OF THE REFERENCE ITSELF (its dataflow simulator
+run in the build container, tests/golden/reference_sim.npz, generator make_reference_sim_golden.py),
+frozen known answers for the reference's test programs (tests/golden/known_answers.json, partly
+hand-derived), the independent C++/OpenMP restatement, and analytic invariants."""
 import json
 import os
 
@@ -14,6 +15,44 @@ from conftest import GOLDEN, HALO, all_programs, program_path, random_inputs
 
 with open(os.path.join(GOLDEN, "known_answers.json")) as _f:
     KNOWN = json.load(_f)
+
+
+with open(os.path.join(GOLDEN, "reference_sim.json")) as _f:
+    REFERENCE_SIM = json.load(_f)
+
+
+def reference_sim_case(case):
+    """(program dict, inputs, {output: array the reference's simulator produced})"""
+    sys_path_golden()
+    import make_reference_sim_golden as gen
+    rec = REFERENCE_SIM[case]
+    prog = gen.case_program(rec["program"])
+    inputs = gen.case_inputs(prog, rec["seed"])
+    with np.load(os.path.join(GOLDEN, "reference_sim.npz")) as z:
+        expected = {o: z[case + "/" + o] for o in rec["outputs"]}
+    return prog, inputs, expected
+
+
+def sys_path_golden():
+    import sys
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+
+
+@pytest.mark.parametrize("case", sorted(REFERENCE_SIM))
+def test_oracles_match_reference_simulator(case):
+    """Both restatements against what the reference's own code computed for the same program and
+    inputs.  The simulator evaluates every operator in Python floats (double) and rounds the result
+    to the operator's data type (kernel.py:716-718), the oracle evaluates in the data type itself:
+    for float32 that is a few ulp per operator, far inside the 1e-5 of arrays_are_equal."""
+    prog, inputs, expected = reference_sim_case(case)
+    got_np = rn.run_reference(prog, inputs)
+    got_cpp = rc.run_reference_cpp(prog, inputs)
+    for field, ref in expected.items():
+        tol = 2e-6 if ref.dtype == np.float32 else 1e-13
+        assert got_np[field].dtype == ref.dtype and got_np[field].shape == ref.shape
+        assert rn.max_relative_error(ref, got_np[field]) <= tol, (case, field)
+        assert rn.max_relative_error(ref, got_cpp[field]) <= 2 * tol, (case, field)
 
 
 @pytest.mark.parametrize("name", sorted(KNOWN))

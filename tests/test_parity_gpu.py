@@ -83,6 +83,32 @@ def test_reference_programs_match_known_answers(gpu, name):
             assert abs(float(arr[tuple(point)]) - value) <= tol * max(1.0, abs(value))
 
 
+with open(os.path.join(GOLDEN, "reference_sim.json")) as _f:
+    REFERENCE_SIM = json.load(_f)
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["planned", "unfused"])
+@pytest.mark.parametrize("case", sorted(REFERENCE_SIM))
+def test_cuda_matches_reference_simulator(gpu, case, fuse):
+    """The CUDA path against OUTPUTS OF THE REFERENCE ITSELF: its dataflow simulator run in the build
+    container on the same program and inputs (tests/golden/reference_sim.npz, generator
+    make_reference_sim_golden.py).  No oracle in between."""
+    import sys
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import make_reference_sim_golden as gen
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    rec = REFERENCE_SIM[case]
+    inputs = gen.case_inputs(gen.case_program(rec["program"]), rec["seed"])
+    got, _ = _run_cuda(rec["program"], inputs, None if fuse else PlanOptions(fuse=False))
+    with np.load(os.path.join(GOLDEN, "reference_sim.npz")) as z:
+        for field in rec["outputs"]:
+            ref = z[case + "/" + field]
+            assert got[field].dtype == ref.dtype
+            assert rn.max_relative_error(ref, got[field]) <= TOL[ref.dtype.name], (case, field)
+
+
 @pytest.mark.parametrize("name,halo", [("ref_jacobi3d_32x32x32_8itr_8vec", 0), ("ref_varying_dimensionality", 0),
                                        ("ref_simulator11", 0), ("hdiff_24x28x16", 2),
                                        ("jacobi2d_96x128_6itr_shrink_f64", 6)])
@@ -302,6 +328,57 @@ def test_pair_sync_and_prefetch_3d(gpu, name, variant):
     got, prog = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, threads_per_row=ks,
                                                     prefetch=p, sync=sync))
     _check(name, got, expected)
+
+
+DIRECT_VARIANTS_3D = [
+    # (max_depth, rows_per_thread, warps, threads per row, prefetch): neighbour rows of the streamed
+    # input read straight from the TMA ring (PlanOptions.direct); the ring depth prefetch + 2 must
+    # divide the unroll factor
+    (4, 3, 12, 16, 4), (4, 4, 8, 16, 4), (2, 4, 8, 32, 1), (3, 2, 8, 16, 1), (1, 4, 8, 32, 1), (4, 4, 8, 32, 4),
+]
+
+
+@pytest.mark.parametrize("variant", DIRECT_VARIANTS_3D, ids=lambda v: "d{}r{}w{}k{}p{}x".format(*v))
+@pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "fork_join_20x16x24", "box3d_10x12x16",
+                                  "jacobi3d_16x24x32_5itr_const1"])
+def test_direct_input_rows_3d(gpu, name, variant):
+    """(jacobi3d_16x24x32_5itr_const1 has a non-zero boundary value: its input needs the fix-up, so the
+    option must leave it on the exchange ring and still be correct.)"""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    d, r, w, ks, p = variant
+    inputs = random_inputs(name, seed=37)
+    expected = rn.run_reference(program_path(name), inputs)
+    got, prog = _run_cuda(name, inputs, PlanOptions(max_depth=d, rows_per_thread=r, warps=w, threads_per_row=ks,
+                                                    prefetch=p, direct=1))
+    _check(name, got, expected)
+    streamed = [l for l in prog.lowered.launches if l.family == "streamed"]
+    if name == "ref_jacobi3d_32x32x32_8itr_8vec" and streamed:
+        assert any(l.info.get("direct") for l in streamed)
+
+
+def test_direct_input_rows_bit_identical_at_scale(gpu):
+    """Many CTAs and waves: reading the input's neighbour rows from the TMA ring must reproduce the
+    exchange-ring kernel bit for bit (a slot recycled too early would show as a difference)."""
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    prog = programs.jacobi3d_chain([320, 448, 512], 8)
+    path = programs.write_program(prog, "direct_jacobi3d")
+    n = int(np.prod(prog["dimensions"]))
+    sums = []
+    for opts in (dict(max_depth=4, rows_per_thread=3, warps=12, prefetch=4),
+                 dict(max_depth=4, rows_per_thread=3, warps=12, prefetch=4, direct=1),
+                 dict(max_depth=4, rows_per_thread=4, warps=8, prefetch=4, direct=1),
+                 dict(max_depth=2, rows_per_thread=4, warps=8, threads_per_row=32, prefetch=1, direct=1)):
+        p = CudaProgram(path, plan_options=PlanOptions(**opts))
+        p.rt.fill_hash(p.buffers["a"].dptr, n, np.float32, seed=99)
+        for _ in range(3):
+            p.execute()
+        p.rt.stream_synchronize()
+        sums.append(p.rt.checksum(p.buffers["b7"].dptr, n, np.float32))
+        p.close()
+    assert all(s[1] == sums[0][1] for s in sums[1:]), sums
 
 
 def test_pair_sync_is_selected_when_asked(native_lib):
