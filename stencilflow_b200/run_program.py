@@ -74,8 +74,21 @@ def run_program(stencil_file,
         print("Creating kernel graph...")
     chain = KernelChainGraph(path=stencil_file, plot_graph=plot, log_level=log_level)
 
+    simulation_result = None
     if run_simulation:
-        print("Note: the cycle-level FPGA simulator is not part of the cuda backend; skipping.")
+        # reference run_program.py:48-61
+        if log_level >= LogLevel.BASIC:
+            print("Running simulation...")
+        from .simulator import Simulator
+        sim_description = program_description
+        if input_directory is not None:
+            sim_description = dict(program_description, path=input_directory)
+        sim = Simulator(program_name=name, program_description=sim_description,
+                        input_nodes=chain.input_nodes, kernel_nodes=chain.kernel_nodes,
+                        output_nodes=chain.output_nodes, dimensions=chain.dimensions,
+                        write_output=False, log_level=log_level)
+        sim.simulate()
+        simulation_result = sim.get_result()
 
     from .cuda_program import CudaProgram
 
@@ -188,4 +201,27 @@ def run_program(stencil_file,
                 print("Got:      {}".format(got))
                 raise ValueError("Result mismatch.")
         print("Results verified.")
-        return 0
+        if simulation_result is None:
+            return 0
+
+    # Compare simulation result to the device result (reference run_program.py:232-250; there it is
+    # skipped when -compare-to-reference already returned, here both checks run)
+    if simulation_result is not None:
+        print("Comparing simulation results...")
+        all_match = True
+        for outp in output_arrays:
+            got = output_arrays[outp]
+            simulated = simulation_result[outp].reshape(program_description["dimensions"])
+            if halo > 0:
+                simulated = simulated[tuple(slice(halo, -halo) for _ in simulated.shape)]
+            if print_result:
+                print("CUDA result:\n\t{}".format(np.ravel(got)))
+                print("Simulation result:\n\t{}".format(np.ravel(simulated)))
+            if not helper.arrays_are_equal(np.ravel(simulated), np.ravel(got),
+                                           tolerance=tolerance_for(got.dtype)):
+                all_match = False
+        if all_match:
+            print("Results verified.")
+            return 0
+        print("Result mismatch.")
+        return 1

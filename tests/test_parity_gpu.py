@@ -123,6 +123,20 @@ def test_run_program_compare_to_reference(gpu, name, halo, tmp_path, monkeypatch
     assert os.path.isdir(tmp_path / "results" / base / "reference")
 
 
+@pytest.mark.parametrize("name,halo,compare", [("ref_simulator12", 0, False), ("ref_jacobi2d_128x128", 0, True),
+                                               ("hdiff_16x20x8_f64", 2, True), ("ref_varying_dimensionality", 0, False)])
+def test_run_program_with_simulation(gpu, name, halo, compare, tmp_path, monkeypatch, capsys):
+    """`run_program.py prog.json cuda -run-simulation`: the dataflow simulator's result is compared with
+    the device result (reference run_program.py:48-61,232-250)."""
+    from stencilflow_b200.run_program import run_program
+    monkeypatch.chdir(tmp_path)
+    ret = run_program(program_path(name), "cuda", run_simulation=True, compare_to_reference=compare, halo=halo,
+                      log_level=0, input_directory=os.path.dirname(program_path(name)))
+    assert ret == 0
+    out = capsys.readouterr().out
+    assert "Comparing simulation results..." in out and "Results verified." in out
+
+
 def test_mismatch_is_detected(gpu, tmp_path, monkeypatch):
     from stencilflow_b200 import run_program as rp
     monkeypatch.chdir(tmp_path)
