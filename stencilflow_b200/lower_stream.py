@@ -1633,7 +1633,7 @@ def choose_chunk(n_stream, tiles, overhead, sms=148):
     """Planes per CTA along the streamed dimension: balance wave quantisation against the
     redundant warm-up planes every chunk recomputes."""
     best = None
-    for chunks in range(1, 65):
+    for chunks in range(1, 65 * max(1, sms // 148)):
         ci = -(-n_stream // chunks)
         blocks = tiles * (-(-n_stream // ci))
         waves = -(-blocks // sms)
@@ -1658,11 +1658,15 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
     gx = -(-NK // geo.BK)
     gy = -(-NJ // geo.BJ) if ana.ndim == 3 else 1
     overhead = ana.t_end_offset() - ana.t_begin_offset()
+    # CTAs of this kernel an SM holds at once: small CTAs (1-4 warps, the warp-private 2-D tiles) share an
+    # SM, limited by the register file (ptxas may use 255 registers under __launch_bounds__(NT, 1)),
+    # shared memory and the 32-CTA limit; the chunking must fill all of those slots
+    resident = max(1, min(65536 // (256 * geo.NT), SMEM_LIMIT // max(geo.smem, 1), 32))
 
     def chunk_for(b, e_):
         if options.chunk:
             return options.chunk
-        return choose_chunk(max(1, e_ - b), gx * gy, overhead)
+        return choose_chunk(max(1, e_ - b), gx * gy, overhead, sms=148 * resident)
 
     def grid(b, e_):
         ci = chunk_for(b, e_)
