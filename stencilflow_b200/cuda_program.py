@@ -281,17 +281,38 @@ class CudaProgram:
     PIPELINE_MIN_BYTES = 64 << 20
 
     def _pipeline_schedule(self, pieces):
+        """:meth:`_pipeline_ranges` with every launch range turned into a parameter pack."""
+        ranges = self._pipeline_ranges(pieces)
+        if ranges is None:
+            return None
+        base = self.slab.alloc_begin if self.slab is not None else 0
+        for step in ranges:
+            step["launch"] = [self._pack_launch(self.lowered.launches[idx], base, b, e)
+                              for (idx, b, e) in step["launch"]]
+        return ranges
+
+    def _pipeline_ranges(self, pieces):
         """Cuts one execution into ``pieces`` along the slab axis so that host->device copies, the
         passes and device->host copies of different pieces overlap (PCIe is full duplex).
 
         Piece s makes input planes < e_s available; every launch then advances as far as the planes
         it reads allow (its output frontier trails its inputs' by its forward reach), so nothing is
-        computed twice and no launch reads a plane that is not final.  Returns None when the plan
-        cannot be cut: no slab axis, an array that does not span it, or intermediates that share
-        storage (a later piece would still need planes an earlier piece's successor overwrote)."""
+        computed twice and no launch reads a plane that is not final.
+
+        On a slab (one rank of a multi-GPU run) the same schedule runs on the rank's own planes without
+        any halo exchange: launch l produces the owned range widened by what the launches after it
+        still reach for (those planes are recomputed redundantly on both neighbours, bit-identically),
+        which needs the buffers to carry the *accumulated* reach of the program as halo
+        (``distributed.total_reach``).
+
+        Returns a list of steps ``{"h2d": [(field, b, e)], "launch": [(launch index, b, e)], "d2h":
+        [(field, b, e)]}`` (plane ranges along the slab axis, global numbering), or None when the plan
+        cannot be cut: no slab axis, an array that does not span it,
+        intermediates that share storage (a later piece would still need planes an earlier piece's
+        successor overwrote), or a slab whose halo is thinner than the accumulated reach."""
         lowered = self.lowered
         axis = lowered.slab_axis
-        if axis is None or self.slab is not None or pieces < 2:
+        if axis is None or pieces < 2:
             return None
         it = "ijk"[axis]
         fields = self.program.fields
@@ -302,42 +323,75 @@ class CudaProgram:
         assign = self.plan.buffer_assignment()
         if len(set(assign.values())) != len(assign):
             return None
+        if self.slab is None:
+            dom0, dom1, own0, own1 = 0, n, 0, n
+        else:
+            dom0, dom1, own0, own1 = self.slab.alloc_begin, self.slab.alloc_end, self.slab.begin, self.slab.end
         from .distributed import launch_reach
-        reach = [launch_reach(lowered, idx) for idx in range(len(lowered.launches))]
-        if n // pieces < 4 * max([1] + [max(r) for rr in reach for r in rr.values()]):
+        launches = lowered.launches
+        reach = [launch_reach(lowered, idx) for idx in range(len(launches))]
+        if (dom1 - dom0) // pieces < 4 * max([1] + [max(r) for rr in reach for r in rr.values()]):
             return None
         inputs = [a for a in arrays if fields[a].kind == "input"]
         outputs = [a for a in arrays if fields[a].kind == "output"]
-        avail = {a: 0 for a in inputs}
-        done = [0] * len(lowered.launches)
-        out_done = {o: 0 for o in outputs}
+        # planes every launch has to produce, and planes of every field somebody needs
+        need = {o: [own0, own1] for o in outputs}
+        target = [None] * len(launches)
+        for idx in range(len(launches) - 1, -1, -1):
+            l = launches[idx]
+            wanted = [need[w] for w in l.writes if w in need]
+            if not wanted:
+                return None
+            lo, hi = min(w[0] for w in wanted), max(w[1] for w in wanted)
+            target[idx] = (lo, hi)
+            for f in l.reads:
+                if fields[f].is_scalar or it not in fields[f].dims:
+                    continue
+                b, fw = reach[idx].get(f, (0, 0))
+                r = need.setdefault(f, [n, 0])
+                r[0], r[1] = min(r[0], max(0, lo - b)), max(r[1], min(n, hi + fw))
+        for a in inputs:
+            need.setdefault(a, [own0, own1])
+            if need[a][0] < dom0 or need[a][1] > dom1:
+                return None
+        avail = {a: need[a][0] for a in inputs}
+        top = {a: need[a][1] for a in inputs}
+        for idx, l in enumerate(launches):
+            for f in l.writes:
+                top[f] = target[idx][1]
+        done = [t[0] for t in target]
+        out_done = {o: own0 for o in outputs}
+        span0 = min(need[a][0] for a in inputs)
+        span1 = max(need[a][1] for a in inputs)
         schedule = []
         for s in range(pieces):
-            e_in = (n * (s + 1)) // pieces
+            e_in = span0 + ((span1 - span0) * (s + 1)) // pieces
             step = {"h2d": [], "launch": [], "d2h": []}
             for a in inputs:
-                step["h2d"].append((a, avail[a], e_in))
-                avail[a] = e_in
-            for idx, l in enumerate(lowered.launches):
-                lim = n
+                e_a = min(max(e_in, avail[a]), need[a][1])
+                step["h2d"].append((a, avail[a], e_a))
+                avail[a] = e_a
+            for idx, l in enumerate(launches):
+                lim = target[idx][1]
                 for f in l.reads:
                     if f not in avail:
                         continue
                     have = avail[f]
                     fwd = reach[idx].get(f, (0, 0))[1]
-                    lim = min(lim, n if have >= n else have - fwd)
+                    lim = min(lim, target[idx][1] if have >= top[f] else have - fwd)
                 lim = max(lim, done[idx])
                 if lim > done[idx]:
-                    step["launch"].append(self._pack_launch(l, 0, done[idx], lim))
+                    step["launch"].append((idx, done[idx], lim))
                     done[idx] = lim
                 for f in l.writes:
                     avail[f] = lim
             for o in outputs:
-                if avail.get(o, 0) > out_done[o]:
-                    step["d2h"].append((o, out_done[o], avail[o]))
-                    out_done[o] = avail[o]
+                e_o = min(avail.get(o, own0), own1)
+                if e_o > out_done[o]:
+                    step["d2h"].append((o, out_done[o], e_o))
+                    out_done[o] = e_o
             schedule.append(step)
-        assert all(d == n for d in done) and all(v == n for v in out_done.values())
+        assert all(d == t[1] for d, t in zip(done, target)) and all(v == own1 for v in out_done.values())
         return schedule
 
     def _call_pipelined(self, arrays, pieces):
@@ -359,9 +413,12 @@ class CudaProgram:
         for name, arr in arrays.items():
             f = fields[name]
             arr = np.asarray(arr)
-            if arr.dtype != f.data_type.type or not arr.flags["C_CONTIGUOUS"] or arr.size != int(np.prod(f.shape)):
+            if (arr.dtype != f.data_type.type or not arr.flags["C_CONTIGUOUS"]
+                    or arr.size != int(np.prod(self.local_shape(name)))):
                 return False
             flat[name] = arr.reshape(-1)
+        base = self.slab.alloc_begin if self.slab is not None else 0     # first plane the buffers hold
+        copied = [0, 0]
         start = rtm.event_create(False)
         rtm.event_record(start)                    # copies must not overtake earlier work on the main stream
         rtm.stream_wait_event(s_in, start)
@@ -371,8 +428,9 @@ class CudaProgram:
                 f = fields[name]
                 plane = int(np.prod(f.shape[1:])) if len(f.shape) > 1 else 1
                 if e > b:
-                    rtm.h2d(self.buffers[name].dptr + b * plane * f.data_type.bytes,
-                            flat[name][b * plane:e * plane], stream=s_in)
+                    rtm.h2d(self.buffers[name].dptr + (b - base) * plane * f.data_type.bytes,
+                            flat[name][(b - base) * plane:(e - base) * plane], stream=s_in)
+                    copied[0] += (e - b) * plane * f.data_type.bytes
             rtm.event_record(ev_in, s_in)
             rtm.stream_wait_event(None, ev_in)
             for l, fn, grid, pack in step["launch"]:
@@ -383,11 +441,13 @@ class CudaProgram:
             for (name, b, e) in step["d2h"]:
                 f = fields[name]
                 plane = int(np.prod(f.shape[1:])) if len(f.shape) > 1 else 1
-                rtm.d2h(flat[name][b * plane:e * plane],
-                        self.buffers[name].dptr + b * plane * f.data_type.bytes, stream=s_out)
+                rtm.d2h(flat[name][(b - base) * plane:(e - base) * plane],
+                        self.buffers[name].dptr + (b - base) * plane * f.data_type.bytes, stream=s_out)
+                copied[1] += (e - b) * plane * f.data_type.bytes
         rtm.stream_synchronize(s_out)
         rtm.stream_synchronize()
         rtm.event_destroy(start)
+        self.last_call_bytes = tuple(copied)           # (host->device, device->host) of this call
         return True
 
     def __call__(self, **kwargs):

@@ -236,19 +236,14 @@ class GroupAnalysis:
         self.aux_reach: Dict[str, List[int]] = {}            # name -> [back, fwd] along the streamed dim
         self.aux_bc: Dict[str, float] = {}
         produced = {op.name for op in ops}
+        # fields of the group that operators outside it read: they have to be written to HBM
         later = set()
-        seen_group = False
         for op in program.ops:
-            if op in ops:
-                seen_group = True
-                continue
-            if seen_group or True:
+            if op not in ops:
                 later.update(f for f in op.accesses if f in produced)
         for op in ops:
             if op.data_type != self.dtype:
                 raise NotStreamable("mixed result types in group")
-            for s in op.scalars:
-                pass
             taps = []
             for field in op.accesses:
                 f = program.fields[field]

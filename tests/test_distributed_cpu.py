@@ -67,3 +67,55 @@ def test_slab_partition():
     assert slabs[3].alloc_end == 1030
     with pytest.raises(ValueError):
         distributed.Slab(0, 8, 16, 4)
+
+
+@pytest.mark.parametrize("world,pieces", [(1, 16), (2, 8), (4, 4), (8, 4)])
+def test_exchange_free_call_schedule(native_lib, world, pieces):
+    """The overlapped host-array call on a slab (CudaProgram._pipeline_ranges): every launch produces
+    exactly the planes later launches and the owned output need, in order, never ahead of its inputs,
+    and only owned output planes travel back -- with no halo exchange, given a halo of the accumulated
+    reach (distributed.total_reach)."""
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    name, prog, _ = programs.baseline_config(1)
+    path = programs.write_program(prog, name)
+    probe = CudaProgram(path, allocate=False)
+    n = 1024
+    wide = distributed.total_reach(probe.lowered)
+    assert wide == 8 and distributed.halo_depth(probe.lowered) == 4       # two passes of four operators
+    for rank in range(world):
+        slab = distributed.Slab(rank, world, n, wide) if world > 1 else None
+        p = CudaProgram(path, allocate=False, slab=slab)
+        steps = p._pipeline_ranges(pieces)
+        assert steps is not None
+        own = (slab.begin, slab.end) if slab else (0, n)
+        produced = {}                      # launch -> [begin, end) so far
+        frontier = {}                      # field -> planes final so far (exclusive)
+        lowest = {}
+        sent_back = []
+        for step in steps:
+            for (f, b, e) in step["h2d"]:
+                assert b == frontier.get(f, b) and e >= b
+                lowest.setdefault(f, b)
+                frontier[f] = e
+            for (idx, b, e) in step["launch"]:
+                l = p.lowered.launches[idx]
+                if idx in produced:
+                    assert b == produced[idx][1]
+                produced[idx] = (produced.get(idx, (b, b))[0], e)
+                for f, (back, fwd) in distributed.launch_reach(p.lowered, idx).items():
+                    assert min(e - 1 + fwd, n - 1) < frontier[f], (idx, f, e, frontier[f])
+                    assert max(b - back, 0) >= lowest[f]
+                for f in l.writes:
+                    lowest.setdefault(f, b)
+                    frontier[f] = e
+            sent_back += step["d2h"]
+        assert produced[len(p.lowered.launches) - 1] == own
+        lo0, hi0 = produced[0]
+        assert lo0 == max(0, own[0] - 4) and hi0 == min(n, own[1] + 4)     # widened by the second pass's reach
+        assert [b for (_, b, _) in sent_back][0] == own[0] and sent_back[-1][2] == own[1]
+        assert all(a[2] == b[1] for a, b in zip(sent_back, sent_back[1:]))
+    # a halo of one pass only is not enough: the call falls back to execute() with halo pushes
+    if world > 1:
+        thin = CudaProgram(path, allocate=False, slab=distributed.Slab(0, world, n, 4))
+        assert thin._pipeline_ranges(pieces) is None

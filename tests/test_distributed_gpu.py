@@ -28,6 +28,7 @@ def _gpu_count(native_lib):
     ("fork_join_20x16x24", True),
     ("lowdim3d_20x24x48_3st_f32", True),
     ("ref_varying_dimensionality", True),
+    ("chain3d:160x64x128", True),
 ])
 def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if _gpu_count(native_lib) < 2:
@@ -39,7 +40,13 @@ def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py"), name, "1" if fuse else "0"]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    env = dict(os.environ)
+    if name.startswith("chain3d"):
+        env["SFB200_PIPELINE_PIECES"] = "4"         # 88 planes per rank: pieces of 22 planes
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-4000:]
     lines = [json.loads(l[len("RESULT "):]) for l in res.stdout.splitlines() if l.startswith("RESULT ")]
     assert len(lines) == 2 and all(l["ok"] for l in lines)
+    if name.startswith("chain3d"):
+        # wide halo (accumulated reach 8) -> the host-array call ran as the overlapped exchange-free schedule
+        assert all(l["halo"] == 8 and l["report"]["call_pipelined"] for l in lines), lines
