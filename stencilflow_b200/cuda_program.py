@@ -318,6 +318,10 @@ class CudaProgram:
         fields = self.program.fields
         n = self.program.shape3[axis]
         arrays = [name for name, f in fields.items() if not f.is_scalar and f.kind in ("input", "output")]
+        # inputs without the slab axis (1-D/2-D coefficient arrays) are small: they go up whole with
+        # the first piece; everything else must have the slab axis outermost
+        whole = [a for a in arrays if fields[a].kind == "input" and it not in fields[a].dims]
+        arrays = [a for a in arrays if a not in whole]
         if any(it not in fields[a].dims or fields[a].dims[0] != it for a in arrays):
             return None
         assign = self.plan.buffer_assignment()
@@ -366,7 +370,7 @@ class CudaProgram:
         schedule = []
         for s in range(pieces):
             e_in = span0 + ((span1 - span0) * (s + 1)) // pieces
-            step = {"h2d": [], "launch": [], "d2h": []}
+            step = {"h2d": [], "launch": [], "d2h": [], "h2d_whole": whole if s == 0 else []}
             for a in inputs:
                 e_a = min(max(e_in, avail[a]), need[a][1])
                 step["h2d"].append((a, avail[a], e_a))
@@ -424,6 +428,9 @@ class CudaProgram:
         rtm.stream_wait_event(s_in, start)
         rtm.stream_wait_event(s_out, start)
         for step, (ev_in, ev_done) in zip(self._pipe, self._pipe_events):
+            for name in step.get("h2d_whole", ()):
+                rtm.h2d(self.buffers[name].dptr, flat[name], stream=s_in)
+                copied[0] += flat[name].nbytes
             for (name, b, e) in step["h2d"]:
                 f = fields[name]
                 plane = int(np.prod(f.shape[1:])) if len(f.shape) > 1 else 1

@@ -1454,7 +1454,9 @@ def candidate_geometries(program, ops, options):
                     if groups and (groups * ks) % 32 == 0 and groups * ks <= 768:
                         out.append((R, groups, 1, ks))
     else:
-        for w in ([options.warps] if options.warps else [8, 16]):
+        # 2-D rows: the warps of a CTA sit side by side; small CTAs (2-4 warps) let several independent
+        # CTAs share an SM, each with its own barrier and TMA ring
+        for w in ([options.warps] if options.warps else [2, 4, 8, 16]):
             out.append((1, 1, w, 32))
     ks = getattr(options, "threads_per_row", 0)
     if ks:
@@ -1469,7 +1471,12 @@ def candidate_geometries(program, ops, options):
 # windows do not fit the register file of the chosen CTA size.
 HBM_BYTES_PER_S = 6.1e12
 UPDATES_PER_S = {4: 2.7e12, 8: 0.95e12}     # computed cell updates per second at R = 4, by element size
+UPDATES_PER_S_2D = {4: 2.7e12, 8: 1.95e12}  # 2-D rows, 8-warp CTAs (float64: 16 operators in 9.07 ms, r01c)
 ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0, 5: 1.0}
+# 2-D rows: compute rate of a CTA of w warps relative to 8 warps, measured on the float64 chain
+# (profiles/r01c_sweep_config3_small_ctas.txt; tile efficiency factored out): independent small CTAs
+# hide each other's barrier and exchange latency
+SMALL_CTA_FACTOR_2D = {1: 1.03, 2: 1.14, 4: 1.06}
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
 
 
@@ -1491,8 +1498,9 @@ def modelled_time(program, ops, ana, geo):
         nj = program.shape[-2]
         used *= nj / float(-(-nj // geo.BJ) * geo.BJ)
     t_mem = nbytes / HBM_BYTES_PER_S
-    rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), UPDATES_PER_S[ana.dtype.bytes]))
-    rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else 1.0
+    table = UPDATES_PER_S if ana.ndim == 3 else UPDATES_PER_S_2D
+    rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), table[ana.dtype.bytes]))
+    rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else SMALL_CTA_FACTOR_2D.get(geo.NT // 32, 1.0)
     t_cmp = program.cells * len(ops) / (eff * used) / rate
     return max(t_mem, t_cmp) + 5e-6
 
@@ -1514,7 +1522,9 @@ def choose_geometry(program, ops, options):
             V, candidates = candidate_geometries(program, ops, opts)
             if V is None:
                 continue
-            prefetch = opts.prefetch or 2
+            # TMA ring depth - 1: 2 planes ahead by default; 2-D rows are small (a ring of 6 fits many
+            # times) and measured fastest with 5 (profiles/r01_sweep_sync_prefetch.txt)
+            prefetch = opts.prefetch or (5 if len(program.shape) == 2 else 2)
             explicit = bool(opts.rows_per_thread and opts.warps)
             for (R, WR, WC, KS) in candidates:
                 try:

@@ -278,7 +278,7 @@ def test_plan_variants_2d(gpu, name, variant, tmp_path):
         assert err <= TOL[ref.dtype.name], "{}:{} max rel err {}".format(name, field, err)
 
 
-@pytest.mark.parametrize("kind", ["jacobi3d", "hdiff", "jacobi2d"])
+@pytest.mark.parametrize("kind", ["jacobi3d", "hdiff", "jacobi2d", "jacobi2d_w1d"])
 def test_pipelined_host_call(gpu, kind, monkeypatch):
     """The host-array call cut into pieces (copies overlapping the passes) gives bit-identical
     results to the plain upload / execute / download sequence, and matches the oracle."""
@@ -292,9 +292,18 @@ def test_pipelined_host_call(gpu, kind, monkeypatch):
         prog, halo = programs.hdiff([384, 256, 80]), 2
         inputs = {"inp": synthetic.fill_hash((384, 256, 80), np.float32, 1, 1.0, 2.0),
                   "coeff": synthetic.fill_hash((384, 256, 80), np.float32, 2, 0.0, 0.05)}
-    else:
+    elif kind == "jacobi2d":
         prog, halo = programs.jacobi2d_chain([2048, 4096], 6), 6
         inputs = {"a": synthetic.fill_hash((2048, 4096), np.float64, 7)}
+    else:
+        # a 1-D coefficient array next to the streamed field: it goes up whole with the first piece
+        prog, halo = programs.jacobi2d_chain([2048, 4096], 6), 6
+        prog["inputs"]["w"] = {"data": "constant:0.9", "data_type": "float64", "input_dims": ["k"]}
+        for op in prog["program"].values():
+            op["computation_string"] = op["computation_string"].replace("0.25 *", "0.25 * w[k] *")
+            op["boundary_conditions"]["w"] = {"type": "shrink"}
+        inputs = {"a": synthetic.fill_hash((2048, 4096), np.float64, 7),
+                  "w": synthetic.fill_hash((4096,), np.float64, 8, 0.5, 1.5)}
     path = programs.write_program(prog, "pipelined_" + kind)
     info = rn.ProgramInfo(rn.load_program(path))
     results = []
