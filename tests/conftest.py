@@ -48,6 +48,7 @@ HALO = {
 INPUT_RANGES = {
     "hdiff_24x28x16": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
     "hdiff_16x20x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
+    "hdiff_const_10x12x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
     # hotspot: coefficients of a stable explicit step (the generator's default 0.5 is not)
     "synth_hotspot2d_48x64_4st_f64": {"sdc": (0.05, 0.1), "r_x": (0.5, 1.0), "r_y": (0.5, 1.0), "r_z": (0.5, 1.0),
                                       "amb": (0.5, 1.0)},

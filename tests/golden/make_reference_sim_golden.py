@@ -60,6 +60,11 @@ CASES = [
     ("synth_fork_16x12x16_5st", "synth_fork_16x12x16_5st", 17),
     ("trig3d_8x10x12_f64", "trig3d_8x10x12_f64", 18),
 ]
+# NOT usable as golden although the simulator runs them: operators with several statements
+# (``d = ...; flx = ... d ...``: hdiff_const_10x12x8_f64, multistmt3d_6x8x10_f64).  ``Calculator.evaluate``
+# drops everything up to the first "=" and evaluates ``tree.body[0]`` only (calculator.py:164-175), i.e. it
+# returns the value of the FIRST statement, which is not what the reference's compiled paths compute
+# (the tasklet runs all statements, stencil/cpu.py:141-179).
 # Outside the envelope (tried, reported by main() as NOT SIMULATED): fork_join_20x16x24 and
 # diamond3d_12x10x16 -- joins of paths of unequal length overflow a delay buffer inside the reference's
 # simulator ("RuntimeError: buffer b overflow occurred", bounded_queue.py:122), every 2-D program

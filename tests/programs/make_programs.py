@@ -120,6 +120,19 @@ def main():
             "v": {"computation_string": "v = u[i,j,k] if u[i,j-1,k] > a[i,j,k] else (u[i,j,k+2] + 0.5 * u[i-2,j,k])",
                   "boundary_conditions": {"u": {"type": "constant", "value": 1.0},
                                           "a": {"type": "constant", "value": 0.25}}, "data_type": "float64"}}})
+    hc = hdiff(10, 12, 8, "float64")
+    for op in hc["program"].values():
+        op["boundary_conditions"] = {k: {"type": "constant", "value": 0.5} for k in op["boundary_conditions"]}
+    dump("hdiff_const_10x12x8_f64", hc)
+    half = {"type": "constant", "value": 0.5}
+    dump("multistmt3d_6x8x10_f64", {
+        "inputs": {"a": {"data": "constant:1.0", "data_type": "float64"}}, "outputs": ["q"], "dimensions": [6, 8, 10],
+        "program": {
+            "p": {"computation_string": "d = a[i+1,j,k] - a[i,j,k]; p = 0.0 if d*(a[i,j+1,k] - a[i,j,k]) > 0.0 else d",
+                  "boundary_conditions": {"a": dict(half)}, "data_type": "float64"},
+            "q": {"computation_string": "q = tan(p[i,j,k-1]) + sinh(p[i,j,k]) / cosh(p[i-1,j,k]) if p[i,j+1,k] <= 0.25 "
+                                        "else (p[i,j,k] if p[i,j,k] >= 0.1 else 2.0*p[i,j,k])",
+                  "boundary_conditions": {"p": dict(half)}, "data_type": "float64"}}})
     dump("diamond3d_12x10x16", {
         "inputs": {"a": {"data": "constant:1.0", "data_type": "float32"},
                    "c": {"data": "constant:0.5", "data_type": "float32"}},

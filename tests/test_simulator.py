@@ -67,7 +67,8 @@ def test_matches_reference_simulator_results_and_cycles(case, tmp_path):
     "ref_jacobi2d_128x128", "ref_varying_dimensionality", "ref_simulator", "ref_simulator7", "ref_simulator11",
     "ref_simple_input_delay_buf", "smooth1d_256", "lowdim2d_32x64", "lowdim3d_20x24x48_3st_f32", "math_ops_8x8x8",
     "jacobi3d_12x12x16_3itr_copy", "jacobi2d_96x128_6itr_shrink_f64", "hdiff_16x20x8_f64",
-    "synth_hotspot2d_48x64_4st_f64", "synth_diffusion_10x12x16_4st", "jacobi2d_64x256_6itr_w1d_const_f32"])
+    "synth_hotspot2d_48x64_4st_f64", "synth_diffusion_10x12x16_4st", "jacobi2d_64x256_6itr_w1d_const_f32",
+    "hdiff_const_10x12x8_f64", "multistmt3d_6x8x10_f64"])
 def test_matches_oracle_outside_the_reference_envelope(name):
     path = program_path(name)
     sim = _simulate(path)
