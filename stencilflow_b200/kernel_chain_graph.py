@@ -364,3 +364,38 @@ class KernelChainGraph:
         print("operation count: {}".format(self.operation_count()))
         print("minimum communication volume: {} bytes".format(self.minimum_communication_volume()))
         print("runtime lower bound: {} cycles".format(self.runtime_lower_bound()))
+
+
+def main(argv=None):
+    """``python -m stencilflow_b200.kernel_chain_graph -stencil_file prog.json [-plot] [-simulate] [-report]
+    [-log-level N]`` -- the debugging entry point of reference kernel_chain_graph.py:777-817."""
+    import argparse
+    import re
+    parser = argparse.ArgumentParser()
+    parser.add_argument("-stencil_file", required=True)
+    parser.add_argument("-plot", action="store_true")
+    parser.add_argument("-log-level", default=LogLevel.MODERATE.value, type=int)
+    parser.add_argument("-report", action="store_true")
+    parser.add_argument("-simulate", action="store_true")
+    args = parser.parse_args(argv)
+    level = LogLevel(args.log_level)
+    description = helper.parse_json(args.stencil_file)
+    chain = KernelChainGraph(path=args.stencil_file, plot_graph=args.plot, log_level=level)
+    sim = None
+    if args.simulate:
+        from .simulator import Simulator
+        sim = Simulator(program_name=re.match(r"[^\.]+", os.path.basename(args.stencil_file)).group(0),
+                        program_description=description, input_nodes=chain.input_nodes,
+                        kernel_nodes=chain.kernel_nodes, output_nodes=chain.output_nodes,
+                        dimensions=chain.dimensions, write_output=False, log_level=level)
+        sim.simulate()
+    if args.report:
+        if level < LogLevel.MODERATE:          # at MODERATE and above the constructor has printed it
+            chain.report(args.stencil_file)
+        if sim is not None:
+            print(sim.report())
+    return chain, sim
+
+
+if __name__ == "__main__":
+    main()

@@ -118,3 +118,13 @@ def test_program_counters_and_report(capsys):
     assert all(o.program_counter == sim.total for o in chain.output_nodes.values())
     text = sim.report()
     assert "channel" in text and "latency" in text
+
+
+def test_kernel_chain_graph_command_line(capsys):
+    """reference kernel_chain_graph.py:777-817: -stencil_file ... -simulate -report"""
+    from stencilflow_b200 import kernel_chain_graph
+    chain, sim = kernel_chain_graph.main(["-stencil_file", program_path("ref_simulator12"), "-simulate", "-report",
+                                          "-log-level", "0"])
+    out = capsys.readouterr().out
+    assert sim.all_done() and "total buffer size" in out and "channel kernelA_kernelB" in out
+    assert np.allclose(sim.get_result()["res"][:3], [20.25, 20.25, 19.25])
