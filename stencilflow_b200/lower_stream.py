@@ -934,11 +934,11 @@ class StreamKernelGen:
                 f=f, slot=slot, WR=g.WR, WC=g.WC, sz=R * n)
             for r in range(R):
                 for q in range(n):
-                    e("sf_sts_if(lane == 0, {base} + {o}, {c});".format(
+                    e("sf_sts_if(lane == 0 && wc > 0, {base} + {o}, {c});".format(
                         base=base, o=r * n + q, c=self.cellref("nv[{}]".format(r), q)), 2)
             for r in range(R):
                 for q in range(n):
-                    e("sf_sts_if(lane == 31, {base} + {o}, {c});".format(
+                    e("sf_sts_if(lane == 31 && wc < {last}, {{base}} + {{o}}, {{c}});".format(last=g.WC - 1).format(
                         base=base, o=(R + r) * n + q, c=self.cellref("nv[{}]".format(r), V - n + q)), 2)
 
     # ------------------------------------------------------------------ lower-dimensional inputs
@@ -1379,19 +1379,19 @@ class StreamKernelGen:
             slot = self.ring_slot("xc_" + f, src.col_ring, age, u)
             n = src.col_reach
             sz = g.R * n
-            # every lane reads the (broadcast) ring word, lanes at the warp edge keep it: no branch
+            # only the lane at a warp edge that has a neighbouring warp reads the ring word (predicated load)
             if nl:
                 base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + max(wc - 1, 0)) * 2 + 1) * {sz} + {o}".format(
                     f=f, slot=slot, WR=g.WR, WC=g.WC, sz=sz, o=rr * n)
                 for q in range(nl):
-                    e("{{ const {T} rv = ({base})[{c}]; if (lane == 0 && wc > 0) l_{tag}[{q}] = rv; }}".format(
-                        T=T, tag=tag, q=q, base=base, c=n - nl + q), 3)
+                    e("if (lane == 0 && wc > 0) l_{tag}[{q}] = ({base})[{c}];".format(
+                        tag=tag, q=q, base=base, c=n - nl + q), 3)
             if nr:
                 base = "xcol_{f} + ((({slot} * {WR} + wr) * {WC} + min(wc + 1, {last})) * 2) * {sz} + {o}".format(
                     f=f, slot=slot, WR=g.WR, WC=g.WC, last=g.WC - 1, sz=sz, o=rr * n)
                 for q in range(nr):
-                    e("{{ const {T} rv = ({base})[{c}]; if (lane == 31 && wc < {lastw}) g_{tag}[{q}] = rv; }}".format(
-                        T=T, tag=tag, q=q, base=base, c=q, lastw=g.WC - 1), 3)
+                    e("if (lane == 31 && wc < {lastw}) g_{tag}[{q}] = ({base})[{c}];".format(
+                        tag=tag, q=q, base=base, c=q, lastw=g.WC - 1), 3)
 
     def _var(self, name, local, op):
         if name in local:
