@@ -1,0 +1,87 @@
+"""Host-side planning decisions (no GPU): the plans the BASELINE configs get, the options that reach
+the generator, the chunking that fills every CTA slot of an SM."""
+import os
+
+import pytest
+
+from conftest import program_path
+
+
+def _program(index, variant=None):
+    import bench
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    bench.VARIANT = variant
+    try:
+        name, prog, _ = bench.build_config(index)
+    finally:
+        bench.VARIANT = None
+    return CudaProgram(programs.write_program(prog, name), allocate=False), prog
+
+
+def test_config1_plan(native_lib):
+    p, prog = _program(1)
+    launches = p.lowered.launches
+    assert [len(l.ops) for l in launches] == [4, 4] and all(l.family == "streamed" for l in launches)
+    info = launches[0].info
+    assert info["tile"] == [72, 64] and info["R"] == 3 and info["prefetch"] == 5 and info["unroll"] == 6
+    assert launches[0].block == (384, 1, 1) and launches[0].smem <= 227 * 1024
+    gx, gy, gz = launches[0].grid_fn(0, 1024)
+    assert (gx, gy) == (19, 16) and gx * gy * gz >= 4 * 148
+    # algorithmic bytes of a pass: the field in, the field out
+    assert launches[0].reads == ["a"] and launches[0].writes == ["b3"]
+
+
+def test_config3_plan_uses_small_independent_ctas(native_lib):
+    p, prog = _program(3)
+    launches = p.lowered.launches
+    assert [len(l.ops) for l in launches] == [8, 8]
+    l = launches[0]
+    assert l.block == (64, 1, 1) and l.info["tile"] == [1, 256] and l.info["prefetch"] == 5
+    # four 2-warp CTAs share an SM (255 registers each): the chunking fills 4 x 148 slots several times over
+    gx, gy, gz = l.grid_fn(0, 32768)
+    assert gx == 137 and gy == 1
+    waves = gx * gz / (4 * 148.0)
+    assert waves >= 4 and (waves - int(waves) > 0.85 or waves == int(waves))
+    overhead = l.info["stream_overhead_planes"]
+    assert overhead * gz <= 0.03 * 32768
+
+
+def test_cost_model_picks_small_ctas_and_depth_for_untuned_2d(native_lib):
+    p, prog = _program(3, "w1d")                      # not in the table of measured plans
+    launches = p.lowered.launches
+    assert [len(l.ops) for l in launches] == [8, 8]
+    assert launches[0].block == (64, 1, 1) and launches[0].info["prefetch"] == 5
+    assert "w" in launches[0].reads                   # the 1-D weight is read by the fused pass itself
+
+
+def test_direct_rows_option_reaches_the_generator(native_lib):
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    path = program_path("ref_jacobi3d_32x32x32_8itr_8vec")
+    on = CudaProgram(path, allocate=False, plan_options=PlanOptions(max_depth=4, rows_per_thread=4, warps=8,
+                                                                     threads_per_row=32, prefetch=4, direct=1))
+    off = CudaProgram(path, allocate=False, plan_options=PlanOptions(max_depth=4, rows_per_thread=4, warps=8,
+                                                                      threads_per_row=32, prefetch=4))
+    assert on.lowered.launches[0].info["direct"] == ["a"] and off.lowered.launches[0].info["direct"] == []
+    # no exchange ring for the input, one more TMA slot instead
+    src_on = on.lowered.kernels[on.lowered.launches[0].kernel].source
+    src_off = off.lowered.kernels[off.lowered.launches[0].kernel].source
+    assert "xrow_f0" not in src_on and "xrow_f0" in src_off
+    # a non-zero boundary value needs the fix-up in registers: the option leaves that input on the ring
+    keep = CudaProgram(program_path("jacobi3d_16x24x32_5itr_const1"), allocate=False,
+                       plan_options=PlanOptions(max_depth=4, rows_per_thread=4, warps=8, threads_per_row=32,
+                                                prefetch=4, direct=1))
+    assert keep.lowered.launches[0].info["direct"] == []
+
+
+def test_environment_knobs(monkeypatch):
+    from stencilflow_b200.planner import PlanOptions
+    for k in PlanOptions.KNOBS:
+        monkeypatch.delenv(k, raising=False)
+    assert PlanOptions().is_default
+    monkeypatch.setenv("SFB200_DIRECT", "1")
+    monkeypatch.setenv("SFB200_SYNC", "pair")
+    o = PlanOptions()
+    assert o.direct == 1 and o.sync == "pair" and not o.is_default
+    assert PlanOptions(direct=0).direct == 0
