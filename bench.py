@@ -127,8 +127,10 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
     workload.  Returns (cell-updates/s, cores, sample description)."""
     from oracle import reference_cpp
     from stencilflow_b200 import programs, synthetic
-    cores = threads or os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank);
+    # SFB200_REF_THREADS overrides.  The count reported is the one the OpenMP runtime really uses.
+    cores = threads or int(os.environ.get("SFB200_REF_THREADS", "0")) or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     name, prog, _ = programs.baseline_config(index, VARIANT)
     full = list(prog["dimensions"])
     nops = len(prog["program"])
@@ -140,6 +142,8 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
 
     iters = ["i", "j", "k"][3 - len(full):]
 
+    used = [cores, 0.0]               # threads the OpenMP runtime uses, seconds of the last timed sample
+
     def run(dims):
         p = json.loads(json.dumps(prog))
         p["dimensions"] = dims
@@ -150,10 +154,12 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
             shape = tuple(n for it, n in zip(iters, dims) if it in cfg.get("input_dims", iters))
             inputs[iname] = synthetic.fill_hash(shape, np.dtype(cfg["data_type"]), 1234 + k, lo, hi)
         ref.allocate_transients()
+        used[0] = ref.threads
         ref(**inputs)                                   # warm (page faults, OpenMP team)
         t0 = time.perf_counter()
         ref(**inputs)
         dt = time.perf_counter() - t0
+        used[1] = dt
         return nops * float(np.prod(dims)) / dt, dt
 
     probe_dims = sized(0.125 if full[0] >= 1024 else 1.0)
@@ -175,7 +181,8 @@ def cpu_reference_rate(index, target_seconds=12.0, threads=None):
         dims = probe_dims
     sample = "{} at {} ({} operators, all transients live), 1 warm + 1 timed execution".format(
         name, "x".join(map(str, dims)), nops)
-    return rate, cores, sample
+    cpu_reference_rate.last_sample_seconds = used[1]
+    return rate, used[0], sample
 
 
 def run_reference_arm(args):
@@ -186,10 +193,12 @@ def run_reference_arm(args):
     t_all0 = time.perf_counter()
     cores = os.cpu_count() or 1
     sample = ""
+    times = []
     for step in range(args.warmup + args.steps):
         rate, cores, sample = cpu_reference_rate(args.config, target_seconds=6.0)
         if step >= args.warmup:
             rates.append(rate)
+            times.append(cpu_reference_rate.last_sample_seconds)
         if time.perf_counter() - t_all0 > 150:
             break
     value = float(np.mean(rates)) if rates else rate
@@ -197,7 +206,9 @@ def run_reference_arm(args):
     dims = prog["dimensions"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(rates), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": len(rates), "warmup": args.warmup,
+        "ms_per_step": (1e3 * float(np.mean(times)) if times else None),     # one bounded sample (see "sample")
+        "higher_is_better": True,
         "scaling": args.scaling or "weak", "vs_baseline": None,
         "dtype": "f64" if "f64" in name else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, prog)},

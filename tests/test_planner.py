@@ -85,3 +85,25 @@ def test_environment_knobs(monkeypatch):
     o = PlanOptions()
     assert o.direct == 1 and o.sync == "pair" and not o.is_default
     assert PlanOptions(direct=0).direct == 0
+
+
+def test_reference_arm_line(monkeypatch):
+    """`bench.py --impl reference`: one JSON line with the contract's keys, timed on all host threads
+    even when the launcher exports OMP_NUM_THREADS=1 (torchrun does), the thread count taken from the
+    OpenMP runtime itself."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env.pop("SFB200_REF_THREADS", None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "0",
+                          "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, text=True, env=env, timeout=300,
+                         check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "stencil_cell_updates_per_s"
+    assert line["unit"] == "cell-updates/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert line["ms_per_step"] > 0 and "32x32x32" in line["config"]["workload"]
