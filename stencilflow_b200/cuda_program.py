@@ -176,40 +176,39 @@ class CudaProgram:
     def _pack_launch(self, l, s_base, s_begin, s_end):
         """(launch, function, grid, parameter pack) of launch ``l`` producing planes
         [s_begin, s_end) of the slab axis, device buffers starting at plane ``s_base``."""
-        if True:
-            vals = []
-            b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
-            for a in l.args:
-                if a[0] == "buf":
-                    vals.append(ctypes.c_void_p(self.buffers[a[1]].dptr))
-                elif a[0] == "scalar":
-                    dt, name = a[1], a[2]
-                    if name not in self.scalar_values:
-                        raise KeyError("scalar input {} was not provided".format(name))
-                    vals.append(np.ctypeslib.as_ctypes_type(dt.type)(self.scalar_values[name]))
-                elif a[0] == "slab":
-                    vals += [ctypes.c_int(s_base), ctypes.c_int(b0), ctypes.c_int(e0)]
-                elif a[0] == "int":
-                    vals.append(ctypes.c_int(a[1]))
-                elif a[0] == "chunk":
-                    vals.append(ctypes.c_int(l.info["chunk_fn"](b0, e0)))
-                elif a[0] == "tmap":
-                    spec = a[1]
-                    buf = self.buffers[spec["field"]]
-                    shape = self.local_shape(spec["field"])
-                    dt = self.program.fields[spec["field"]].data_type
-                    dims = list(reversed(shape))
-                    strides = []
-                    acc = dt.bytes
-                    for d in dims[:-1]:
-                        acc *= d
-                        strides.append(acc)
-                    box = list(spec["box"])
-                    vals.append(self.rt.tensor_map(buf.dptr, dt, dims, strides, box))
-                else:
-                    raise ValueError(a)
-            pack = rt.pack_params(vals)
-            return (l, self.functions[l.kernel], l.grid_fn(b0, e0), pack)
+        vals = []
+        b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
+        for a in l.args:
+            if a[0] == "buf":
+                vals.append(ctypes.c_void_p(self.buffers[a[1]].dptr))
+            elif a[0] == "scalar":
+                dt, name = a[1], a[2]
+                if name not in self.scalar_values:
+                    raise KeyError("scalar input {} was not provided".format(name))
+                vals.append(np.ctypeslib.as_ctypes_type(dt.type)(self.scalar_values[name]))
+            elif a[0] == "slab":
+                vals += [ctypes.c_int(s_base), ctypes.c_int(b0), ctypes.c_int(e0)]
+            elif a[0] == "int":
+                vals.append(ctypes.c_int(a[1]))
+            elif a[0] == "chunk":
+                vals.append(ctypes.c_int(l.info["chunk_fn"](b0, e0)))
+            elif a[0] == "tmap":
+                spec = a[1]
+                buf = self.buffers[spec["field"]]
+                shape = self.local_shape(spec["field"])
+                dt = self.program.fields[spec["field"]].data_type
+                dims = list(reversed(shape))
+                strides = []
+                acc = dt.bytes
+                for d in dims[:-1]:
+                    acc *= d
+                    strides.append(acc)
+                box = list(spec["box"])
+                vals.append(self.rt.tensor_map(buf.dptr, dt, dims, strides, box))
+            else:
+                raise ValueError(a)
+        pack = rt.pack_params(vals)
+        return (l, self.functions[l.kernel], l.grid_fn(b0, e0), pack)
 
     def execute(self, stream=None):
         """Enqueue every launch of the plan (asynchronous)."""
