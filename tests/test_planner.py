@@ -107,3 +107,46 @@ def test_reference_arm_line(monkeypatch):
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert line["ms_per_step"] > 0 and "32x32x32" in line["config"]["workload"]
+
+
+def test_choose_chunk_balances_waves_and_warmup():
+    from stencilflow_b200.lower_stream import choose_chunk
+    # 304 tiles of config 1, 8 warm-up planes per chunk, one CTA per SM
+    ci = choose_chunk(1024, 304, 8, sms=148)
+
+    def cost(c):                                  # rounds of CTAs x planes each CTA streams
+        return -(-(304 * -(-1024 // c)) // 148) * (c + 8)
+    assert cost(ci) == min(cost(-(-1024 // n)) for n in range(1, 65)) and 8.0 / ci < 0.08
+    # a single tile column must be cut into many chunks to occupy the machine at all
+    ci = choose_chunk(32768, 1, 16, sms=148)
+    assert -(-32768 // ci) >= 60
+    # more resident CTAs per SM -> more, shorter chunks
+    assert choose_chunk(32768, 137, 16, sms=4 * 148) < choose_chunk(32768, 137, 16, sms=148)
+
+
+@pytest.mark.parametrize("name,depth,expect", [
+    ("ref_jacobi3d_32x32x32_8itr_8vec", 4, (4, 8)),      # two passes of four: 4 per pass, 8 in total
+    ("ref_jacobi3d_32x32x32_8itr_8vec", 2, (2, 8)),
+    ("ref_jacobi3d_32x32x32_8itr_8vec", 8, (8, 8)),
+    ("hdiff_24x28x16", 4, (2, 2)),                        # lap -> flx/fly -> out reaches 2 planes along i
+])
+def test_halo_depth_and_total_reach(native_lib, name, depth, expect):
+    from stencilflow_b200 import distributed
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    p = CudaProgram(program_path(name), allocate=False, plan_options=PlanOptions(max_depth=depth))
+    assert (distributed.halo_depth(p.lowered), distributed.total_reach(p.lowered)) == expect
+
+
+def test_halo_schedule_of_a_two_pass_chain(native_lib):
+    from stencilflow_b200 import distributed
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    p = CudaProgram(program_path("ref_jacobi3d_32x32x32_8itr_8vec"), allocate=False,
+                    plan_options=PlanOptions(max_depth=4))
+    middle = distributed.Slab(1, 4, 32, 4)
+    sends = distributed.halo_schedule(p.lowered, middle)
+    # only the first pass's result crosses slab boundaries: 4 planes up, 4 planes down
+    assert sorted((s.launch, s.field, s.peer, s.src_end - s.src_begin) for s in sends) == \
+        [(0, "b3", 0, 4), (0, "b3", 2, 4)]
+    assert distributed.halo_schedule(p.lowered, distributed.Slab(0, 1, 32, 4)) == []
