@@ -90,6 +90,7 @@ class CudaProgram:
         self.functions = {}
         self.buffers = {}          # field -> DeviceBuffer
         self._owned = []
+        self._tables = []          # work tables of persistent launches (device memory)
         self._packs = None
         self._graph = None
         self.scalar_values = {}
@@ -143,9 +144,9 @@ class CudaProgram:
         if self._graph is not None:
             self.rt.graph_destroy(self._graph)
             self._graph = None
-        for p in self._owned:
+        for p in self._owned + self._tables:
             self.rt.free(p)
-        self._owned = []
+        self._owned, self._tables = [], []
         self.buffers = {}
         if self.module is not None:
             self.rt.module_unload(self.module)
@@ -171,11 +172,13 @@ class CudaProgram:
 
     def _build_packs(self):
         s_base, s_begin, s_end = self._slab_range()
-        self._packs = [self._pack_launch(l, s_base, s_begin, s_end) for l in self.lowered.launches]
+        self._packs = [self._pack_launch(l, s_base, s_begin, s_end, push=True) for l in self.lowered.launches]
 
-    def _pack_launch(self, l, s_base, s_begin, s_end):
+    def _pack_launch(self, l, s_base, s_begin, s_end, push=False):
         """(launch, function, grid, parameter pack) of launch ``l`` producing planes
-        [s_begin, s_end) of the slab axis, device buffers starting at plane ``s_base``."""
+        [s_begin, s_end) of the slab axis, device buffers starting at plane ``s_base``.  ``push``: let a
+        slab kernel store its edge planes into the neighbouring GPUs' halos (``SlabProgram.execute``
+        only; ``push_fn`` is installed by the slab program)."""
         vals = []
         b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
         for a in l.args:
@@ -192,6 +195,17 @@ class CudaProgram:
                 vals.append(ctypes.c_int(a[1]))
             elif a[0] == "chunk":
                 vals.append(ctypes.c_int(l.info["chunk_fn"](b0, e0)))
+            elif a[0] == "push":
+                fn_ = getattr(self, "push_fn", None) if push else None
+                d_lo, d_hi, lo_end, hi_begin = fn_(l, a[1]) if fn_ else (0, 0, -(2 ** 31), 2 ** 31 - 1)
+                vals += [ctypes.c_longlong(d_lo), ctypes.c_longlong(d_hi), ctypes.c_int(lo_end), ctypes.c_int(hi_begin)]
+            elif a[0] == "worktab":
+                table = np.asarray(l.info["work_fn"](b0, e0, self._resident_ctas(l)), dtype=np.int32)
+                dptr = self.rt.malloc(table.nbytes)
+                self._tables.append(dptr)
+                self.rt.h2d(dptr, table)
+                self.rt.stream_synchronize()
+                vals.append(ctypes.c_void_p(dptr))
             elif a[0] == "tmap":
                 spec = a[1]
                 buf = self.buffers[spec["field"]]
@@ -208,7 +222,23 @@ class CudaProgram:
             else:
                 raise ValueError(a)
         pack = rt.pack_params(vals)
-        return (l, self.functions[l.kernel], l.grid_fn(b0, e0), pack)
+        if l.info.get("persistent"):
+            grid = l.grid_fn(b0, e0, self._resident_ctas(l))
+        else:
+            grid = l.grid_fn(b0, e0)
+        return (l, self.functions[l.kernel], grid, pack)
+
+    def _resident_ctas(self, l):
+        """CTA slots of the device for a persistent streamed kernel: SMs x the occupancy the driver
+        reports for the loaded function (one CTA per slot streams an equal share of the pass)."""
+        cache = self.__dict__.setdefault("_slots", {})
+        if l.kernel not in cache:
+            per_sm = self.rt.occupancy(self.functions[l.kernel], l.block[0], l.smem)
+            if per_sm < 1:
+                raise rt.SfbError(-1, "kernel {} does not fit an SM ({} threads, {} bytes of shared memory)".format(
+                    l.kernel, l.block[0], l.smem))
+            cache[l.kernel] = per_sm * int(self.rt.props.sm_count)
+        return cache[l.kernel]
 
     def execute(self, stream=None):
         """Enqueue every launch of the plan (asynchronous)."""

@@ -2,19 +2,31 @@
 
 The reference scales across devices by cutting the *operator pipeline* in two and streaming whole
 fields through SMI channels (``split_sdfg``, ``stencilflow/sdfg_generator.py:680-1000``;
-``bin/run_distributed_program.py``).  On a box of NVLink-connected GPUs the natural decomposition is
+``bin/run_distributed_program.py``); its remote streams run concurrently with the compute pipeline
+(``sdfg_generator.py:846-853``).  On a box of NVLink-connected GPUs the natural decomposition is
 spatial instead: rank g owns planes ``[g*N/G, (g+1)*N/G)`` of the outermost dimension (i for 3-D, j for
-2-D programs); row-major layout makes every halo one contiguous block.  After a pass has written a
-field that a later pass reads with an offset along the slab axis, each rank *pushes* its edge planes
-straight into the halo region of its neighbours' buffers (peer ``cudaMemcpyAsync`` over NVLink on
-IPC-mapped memory) and raises a flag in the neighbour's memory (``cuStreamWriteValue32``); the
-neighbour's stream waits on that flag (``cuStreamWaitValue32``) before launching the consumer.  No host
-synchronisation and no collective is involved; results are bit-identical to the single-GPU run
-because every cell is computed by the same instruction sequence.
+2-D programs); row-major layout makes every halo one contiguous block.  A field that a later pass
+reads across the slab boundary reaches the neighbours' halo planes in one of two ways:
+
+* **in-kernel push** (streamed passes): the producing kernel stores the few planes next to a slab
+  boundary a second time, straight into the neighbour's buffer (peer stores over NVLink on IPC-mapped
+  memory) -- the transfer rides along with the pass tile by tile, nothing is copied afterwards;
+* **copy push** (one-operator kernels): peer ``cudaMemcpyAsync`` of the edge planes on a separate
+  communication stream, ordered behind the producing launch by an event.
+
+Either way the data path is flag-ordered, with no host synchronisation and no collective (``ExchangePlan``):
+after the push a counter is raised in the neighbour's memory (``cuStreamWriteValue32``) and the
+neighbour's consumer launch waits for it (``cuStreamWaitValue32``, >=); a second counter per
+neighbour publishes how far that neighbour's own launches have come, which is what a pusher waits
+for before it overwrites halo planes a launch over there may still be reading.  Exchange
+participation is a property of the *plan*, identical on every rank (a rank with a one-sided reach
+still receives, still counts), and results are bit-identical to the single-GPU run because every
+cell is computed by the same instruction sequence.
 
 One process per GPU.  Rendezvous (exchange of IPC handles, barriers, max-reduction of timings) goes
-through a tiny ``Comm`` interface; ``TorchComm`` implements it with ``torch.distributed`` (gloo), which
-is how ``torchrun`` launches ``bench.py``.  Torch never touches device memory or the data path.
+through a tiny ``Comm`` interface: ``SocketComm`` (plain TCP on 127.0.0.1, no dependencies) or
+``TorchComm`` (``torch.distributed``/gloo, which is how ``torchrun`` launches ``bench.py``).  Neither
+touches device memory or the data path.
 """
 
 import os
@@ -138,6 +150,94 @@ def halo_schedule(lowered, slab: Slab) -> List[HaloSend]:
     return sends
 
 
+class ExchangePlan:
+    """What the launches of a plan exchange across slab boundaries, and the counter values that order
+    it.  Everything here is derived from the plan alone, so every rank computes the same object; only
+    ``for_rank`` looks at who has which neighbour.
+
+    ``up[idx]`` / ``down[idx]``: ``[(field, planes)]`` -- after launch ``idx`` the top ``planes`` owned
+    planes of ``field`` go up (to rank + 1, as its lower halo), resp. the bottom ``planes`` go down.
+    Channel counters: the k-th launch with an ``up`` entry raises the receiver's *from-below* counter
+    to ``rep * len(up_events) + k + 1`` in repetition ``rep`` of the program; likewise *from-above*.
+    Progress counter: after launch ``idx`` of repetition ``rep`` a rank tells both neighbours
+    ``rep * n_launches + idx + 1`` (only after launches somebody waits for, ``progress_points``)."""
+
+    def __init__(self, lowered, storage=None):
+        self.n = len(lowered.launches)
+        self.up = [[] for _ in range(self.n)]
+        self.down = [[] for _ in range(self.n)]
+        storage = storage or {}
+        if lowered.slab_axis is not None:
+            reach = [launch_reach(lowered, idx) for idx in range(self.n)]
+            for idx, l in enumerate(lowered.launches):
+                for field in l.writes:
+                    back = fwd = 0
+                    for later in range(idx + 1, self.n):
+                        r = reach[later].get(field)
+                        if r:
+                            back, fwd = max(back, r[0]), max(fwd, r[1])
+                    if back:
+                        self.up[idx].append((field, back))
+                    if fwd:
+                        self.down[idx].append((field, fwd))
+        self.up_events = [idx for idx in range(self.n) if self.up[idx]]
+        self.down_events = [idx for idx in range(self.n) if self.down[idx]]
+        # before launch j: how many up / down events of this repetition must have arrived
+        self.need_up = [sum(1 for e in self.up_events if e < j) for j in range(self.n)]
+        self.need_down = [sum(1 for e in self.down_events if e < j) for j in range(self.n)]
+        # write-after-read at the receiver: the halo planes of ``field`` (storage S) may only be
+        # overwritten once every launch over there that read the previous content of S is done --
+        # the last reader before ``idx`` in program order, wrapping into the previous repetition
+        readers = {}
+        for j, l in enumerate(lowered.launches):
+            for f in l.reads:
+                readers.setdefault(storage.get(f, f), set()).add(j)
+        self.war = []                  # per launch: (repetition offset 0 / -1, launch index) or None
+        for idx in range(self.n):
+            last = None
+            for (field, _) in self.up[idx] + self.down[idx]:
+                rs = readers.get(storage.get(field, field), set())
+                before = [j for j in rs if j < idx]
+                after = [j for j in rs if j > idx]
+                cand = (0, max(before)) if before else ((-1, max(after)) if after else None)
+                if cand is not None and (last is None or cand > last):
+                    last = cand
+            self.war.append(last)
+        self.progress_points = sorted({w[1] for w in self.war if w is not None})
+
+    def arrival_value(self, channel, rep, idx):
+        events = self.up_events if channel == "up" else self.down_events
+        return rep * len(events) + events.index(idx) + 1
+
+    def wait_values(self, rep, idx):
+        """(from-below, from-above) counter values launch ``idx`` of repetition ``rep`` needs (0 = none)."""
+        lo = rep * len(self.up_events) + self.need_up[idx] if self.need_up[idx] else 0
+        hi = rep * len(self.down_events) + self.need_down[idx] if self.need_down[idx] else 0
+        return lo, hi
+
+    def war_value(self, rep, idx):
+        """Progress a neighbour must have reported before launch ``idx`` of repetition ``rep`` pushes
+        into its halo planes (0 = nothing to wait for)."""
+        w = self.war[idx]
+        if w is None:
+            return 0
+        return max(0, (rep + w[0]) * self.n + w[1] + 1)
+
+    def for_rank(self, slab: Slab):
+        """``[(launch, field, peer, src_begin, src_end)]`` this rank pushes, as :class:`HaloSend`."""
+        sends = []
+        if slab.world == 1:
+            return sends
+        for idx in range(self.n):
+            for (field, back) in self.up[idx]:
+                if slab.rank + 1 < slab.world:
+                    sends.append(HaloSend(idx, field, slab.rank + 1, slab.end - back, slab.end))
+            for (field, fwd) in self.down[idx]:
+                if slab.rank > 0:
+                    sends.append(HaloSend(idx, field, slab.rank - 1, slab.begin, slab.begin + fwd))
+        return sends
+
+
 # ------------------------------------------------------------------------------------ rendezvous
 
 
@@ -206,6 +306,11 @@ class SlabProgram:
         from . import planner
         self.comm = comm
         chain = KernelChainGraph(stencil_file)
+        if plan_options is None:
+            plan_options = planner.PlanOptions()
+        # streamed passes push their edge planes into the neighbours' halos themselves (SFB200_PEER_PUSH=0:
+        # peer copies on the communication streams for every launch, the path one-operator kernels take)
+        plan_options.peer_push = comm.world > 1 and os.environ.get("SFB200_PEER_PUSH", "1") != "0"
         probe = planner.plan_program(make_program(chain), options=plan_options)
         axis = probe.lowered.slab_axis
         if axis is None:
@@ -224,10 +329,14 @@ class SlabProgram:
         self.plan = self.inner.plan
         self.lowered = self.inner.lowered
         self.buffers = self.inner.buffers
-        self.sends = halo_schedule(self.lowered, self.slab)
-        self.comm_stream = self.rt.stream
+        self.xplan = ExchangePlan(self.lowered, self.plan.buffer_assignment())
+        self.sends = self.xplan.for_rank(self.slab)
+        self.comm_streams = {}                 # peer rank -> stream of the copy pushes towards it
+        self._push_events = {}                 # (storage id, peer) -> event of the last copy push that read it
+        self._launch_events = {}               # launch index [, peer] -> event behind the launch [its copy push]
+        self.rep = 0                           # executions so far (the counters never restart)
         self._setup_peers()
-        self.exchange_seq = 0
+        self.inner.push_fn = self._push_params
 
     # -- forwarding
     def local_shape(self, name):
@@ -265,10 +374,15 @@ class SlabProgram:
         return (not f.is_scalar) and ("ijk"[self.lowered.slab_axis] in f.dims)
 
     # -- peers
+    F_BELOW, F_ABOVE, P_LOWER, P_UPPER = 0, 4, 8, 12     # byte offsets of the four counters in ``flags``
+
     def _setup_peers(self):
         rt = self.rt
-        self.flags = rt.malloc(256)                      # [0]: halo from lower, [1]: halo from upper,
-        rt.memset(self.flags, 0, 256)                    # [2]: lower neighbour done, [3]: upper neighbour done
+        # counters other ranks write into this rank's memory: [0] pushes arrived from below (the lower
+        # neighbour's "up" channel), [1] from above, [2] progress of the lower neighbour's launches,
+        # [3] progress of the upper neighbour's
+        self.flags = rt.malloc(256)
+        rt.memset(self.flags, 0, 256)
         rt.stream_synchronize()
         storage = {}
         for name, buf in self.buffers.items():
@@ -289,58 +403,114 @@ class SlabProgram:
                     ptrs[name] = opened[handle]
                 self.peers[peer] = {"flags": rt.ipc_open_handle(info["flags"]), "buffers": ptrs,
                                     "alloc_begin": info["alloc_begin"]}
+                self.comm_streams[peer] = rt.stream_create()
         self._opened = list(opened.values()) + [p["flags"] for p in self.peers.values()]
         self.comm.barrier()
 
+    INT_MIN, INT_MAX = -(2 ** 31), 2 ** 31 - 1
+
+    def _push_params(self, l, field):
+        """Kernel arguments of the in-kernel push of ``field`` by launch ``l``: byte distance from this
+        rank's buffer to the lower / upper neighbour's (same cell), and the plane thresholds -- planes
+        below ``lo_end`` also go down, planes from ``hi_begin`` on also go up."""
+        idx = self.lowered.launches.index(l)
+        f = self.program.fields[field]
+        plane_bytes = self._plane_elems(field) * f.data_type.bytes
+        mine = self.buffers[field].dptr
+        d_lo = d_hi = 0
+        lo_end, hi_begin = self.INT_MIN, self.INT_MAX
+        lower, upper = self.peers.get(self.comm.rank - 1), self.peers.get(self.comm.rank + 1)
+        for (name, fwd) in self.xplan.down[idx]:
+            if name == field and lower is not None:
+                d_lo = lower["buffers"][field] - mine + (self.slab.alloc_begin - lower["alloc_begin"]) * plane_bytes
+                lo_end = self.slab.begin + fwd
+        for (name, back) in self.xplan.up[idx]:
+            if name == field and upper is not None:
+                d_hi = upper["buffers"][field] - mine + (self.slab.alloc_begin - upper["alloc_begin"]) * plane_bytes
+                hi_begin = self.slab.end - back
+        return d_lo, d_hi, lo_end, hi_begin
+
     # -- execution
     def execute(self):
-        """All launches of the program on the owned slab, halos pushed to the neighbours after every
-        launch whose result a later launch reads across the slab boundary."""
-        inner, rt = self.inner, self.rt
+        """All launches of the program on the owned slab.  Fields a later launch reads across the slab
+        boundary reach the neighbours' halo planes from inside the producing kernel (streamed passes)
+        or by peer copies on the communication streams (one-operator kernels); counters in the
+        neighbours' memory order producers, consumers and the reuse of halo storage (``ExchangePlan``)."""
+        inner, rt, x = self.inner, self.rt, self.xplan
         if inner._packs is None:
             inner._build_packs()
         stream = rt.stream
-        rank, world = self.comm.rank, self.comm.world
+        rank = self.comm.rank
+        rep = self.rep
+        self.rep += 1
+        lower, upper = self.peers.get(rank - 1), self.peers.get(rank + 1)
+        flags = self.flags
+        assign = self.plan.buffer_assignment()
         by_launch: Dict[int, List[HaloSend]] = {}
         for s in self.sends:
             by_launch.setdefault(s.launch, []).append(s)
-        lower, upper = self.peers.get(rank - 1), self.peers.get(rank + 1)
         for idx, (l, fn, grid, pack) in enumerate(inner._packs):
+            # read-after-write: the halos this launch reads must have arrived
+            need_lo, need_hi = x.wait_values(rep, idx)
+            if lower is not None and need_lo:
+                rt.wait_flag(stream, flags + self.F_BELOW, need_lo)
+            if upper is not None and need_hi:
+                rt.wait_flag(stream, flags + self.F_ABOVE, need_hi)
+            sends = by_launch.get(idx, [])
+            in_kernel = bool(l.info.get("peer_push")) and bool(sends)
+            war = x.war_value(rep, idx)
+            if in_kernel and war:
+                # the kernel itself writes into the neighbours' halo planes: their last readers must be done
+                for peer in sorted({s.peer for s in sends}):
+                    rt.wait_flag(stream, flags + (self.P_LOWER if peer < rank else self.P_UPPER), war)
+            # a copy push of an earlier launch may still be reading storage this launch overwrites
+            for f in l.writes:
+                for peer in self.peers:
+                    ev = self._push_events.pop((assign.get(f, f), peer), None)
+                    if ev is not None:
+                        rt.stream_wait_event(stream, ev)
             rt.launch(fn, grid, l.block, l.smem, pack.array, stream)
-            sends = by_launch.get(idx)
-            if sends is None:
-                continue
-            self.exchange_seq += 1
-            seq = self.exchange_seq
-            # the neighbours must have finished everything that could still read the halo regions
-            # about to be overwritten: they acknowledge the previous exchange before we push
-            if seq > 1:
+            if in_kernel:
+                if x.up[idx] and upper is not None:
+                    rt.write_flag(stream, upper["flags"] + self.F_BELOW, x.arrival_value("up", rep, idx))
+                if x.down[idx] and lower is not None:
+                    rt.write_flag(stream, lower["flags"] + self.F_ABOVE, x.arrival_value("down", rep, idx))
+            elif sends:
+                ev = self._launch_events.get(idx)
+                if ev is None:
+                    ev = self._launch_events[idx] = rt.event_create(False)
+                rt.event_record(ev, stream)
+                for peer in sorted({s.peer for s in sends}):
+                    cs = self.comm_streams[peer]
+                    rt.stream_wait_event(cs, ev)
+                    if war:
+                        rt.wait_flag(cs, flags + (self.P_LOWER if peer < rank else self.P_UPPER), war)
+                    for s in sends:
+                        if s.peer != peer:
+                            continue
+                        f = self.program.fields[s.field]
+                        plane_bytes = self._plane_elems(s.field) * f.data_type.bytes
+                        info = self.peers[peer]
+                        src = self.buffers[s.field].dptr + (s.src_begin - self.slab.alloc_begin) * plane_bytes
+                        dst = info["buffers"][s.field] + (s.src_begin - info["alloc_begin"]) * plane_bytes
+                        rt.d2d(dst, src, (s.src_end - s.src_begin) * plane_bytes, cs)
+                    if peer > rank:
+                        rt.write_flag(cs, info["flags"] + self.F_BELOW, x.arrival_value("up", rep, idx))
+                    else:
+                        rt.write_flag(cs, info["flags"] + self.F_ABOVE, x.arrival_value("down", rep, idx))
+                    done = self._launch_events.get((idx, peer))
+                    if done is None:
+                        done = self._launch_events[(idx, peer)] = rt.event_create(False)
+                    rt.event_record(done, cs)
+                    for s in sends:
+                        if s.peer == peer:
+                            self._push_events[(assign.get(s.field, s.field), peer)] = done
+            if idx in x.progress_points:
+                value = rep * x.n + idx + 1
                 if lower is not None:
-                    rt.wait_flag(stream, self.flags + 8, seq - 1)
+                    rt.write_flag(stream, lower["flags"] + self.P_UPPER, value)     # I am their upper neighbour
                 if upper is not None:
-                    rt.wait_flag(stream, self.flags + 12, seq - 1)
-            for s in sends:
-                f = self.program.fields[s.field]
-                plane_bytes = self._plane_elems(s.field) * f.data_type.bytes
-                peer = self.peers[s.peer]
-                src = self.buffers[s.field].dptr + (s.src_begin - self.slab.alloc_begin) * plane_bytes
-                dst = peer["buffers"][s.field] + (s.src_begin - peer["alloc_begin"]) * plane_bytes
-                rt.d2d(dst, src, (s.src_end - s.src_begin) * plane_bytes, stream)
-            # tell the neighbours their halos are in place, then wait for ours
-            if upper is not None:
-                rt.write_flag(stream, upper["flags"] + 0, seq)      # I am their lower neighbour
-            if lower is not None:
-                rt.write_flag(stream, lower["flags"] + 4, seq)      # I am their upper neighbour
-            if lower is not None:
-                rt.wait_flag(stream, self.flags + 0, seq)
-            if upper is not None:
-                rt.wait_flag(stream, self.flags + 4, seq)
-            # acknowledge: everything I launched before this point has consumed its halos once the
-            # stream reaches here, so the neighbours may overwrite them at the next exchange
-            if lower is not None:
-                rt.write_flag(stream, lower["flags"] + 12, seq)     # I am their upper neighbour
-            if upper is not None:
-                rt.write_flag(stream, upper["flags"] + 8, seq)      # I am their lower neighbour
+                    rt.write_flag(stream, upper["flags"] + self.P_LOWER, value)     # I am their lower neighbour
         inner.launch_count += len(inner._packs)
 
     # -- the reference-facing call with host arrays
@@ -363,15 +533,34 @@ class SlabProgram:
         h2d = d2h = 0
         for name, f in fields.items():
             if f.kind == "input" and not f.is_scalar:
-                arr = np.ascontiguousarray(np.asarray(arrays[name], dtype=f.data_type.type))
-                rt.h2d(self.buffers[name].dptr, arr.reshape(-1))
-                h2d += arr.nbytes
+                if name not in arrays:
+                    raise KeyError("input array {} was not provided".format(name))
+                n = int(np.prod(self.local_shape(name)))
+                arr = np.ascontiguousarray(np.asarray(arrays[name], dtype=f.data_type.type)).reshape(-1)
+                if arr.size < n:
+                    raise ValueError("input {} has {} elements, this rank's slab needs {}".format(name, arr.size, n))
+                rt.h2d(self.buffers[name].dptr, arr[:n])
+                h2d += n * f.data_type.bytes
         self.execute()
         for name in self.program.outputs:
-            if name in arrays:
-                out = arrays[name].reshape(-1)
-                rt.d2h(out, self.buffers[name].dptr)
-                d2h += out.nbytes
+            if name not in arrays:
+                continue
+            f = fields[name]
+            out = np.asarray(arrays[name])
+            n = int(np.prod(self.local_shape(name)))
+            if out.size != n or out.dtype != f.data_type.type or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("output array for {} must be C-contiguous {} of {} elements".format(
+                    name, f.data_type, n))
+            flat = out.reshape(-1)
+            # owned planes only: the halo planes of the device buffer hold the neighbours' data
+            if self._is_sharded(name):
+                plane = self._plane_elems(name)
+                lo = (self.slab.begin - self.slab.alloc_begin) * plane
+                hi = (self.slab.end - self.slab.alloc_begin) * plane
+            else:
+                lo, hi = 0, n
+            rt.d2h(flat[lo:hi], self.buffers[name].dptr + lo * f.data_type.bytes)
+            d2h += (hi - lo) * f.data_type.bytes
         rt.stream_synchronize()
         self.last_call_bytes = (h2d, d2h)
 
@@ -414,5 +603,8 @@ class SlabProgram:
                 self.rt.ipc_close_handle(p)
             except Exception:
                 pass
+        for ev in self._launch_events.values():
+            self.rt.event_destroy(ev)
+        self._launch_events, self._push_events = {}, {}
         self.rt.free(self.flags)
         self.inner.close()

@@ -194,6 +194,15 @@ class NotStreamable(Exception):
     pass
 
 
+SM_COUNT = 148              # B200; the runtime overwrites it with the device's count when it initialises
+
+
+def persistent_default():
+    """Persistent CTAs (one per SM slot, each streaming an equal share of the (tile, plane) space) unless
+    ``SFB200_PERSISTENT=0`` asks for the one-CTA-per-(tile, chunk) grid."""
+    return os.environ.get("SFB200_PERSISTENT", "1") != "0"
+
+
 class _FieldInfo:
     def __init__(self, name, kind, dtype):
         self.name = name
@@ -502,6 +511,8 @@ class Geometry:
                 off = (off + 127) & ~127
         self.bar_off = off
         off += 8 * self.D * (self.NW if self.pair else 1)
+        self.item_off = off            # persistent CTAs: the work item thread 0 fetched for everybody
+        off += 16
         return off
 
 
@@ -525,7 +536,7 @@ class StreamKernelGen:
     """
 
     def __init__(self, program: StencilProgram, ops: List[StencilOp], ana: GroupAnalysis, geo: Geometry,
-                 specialize=None, max_unroll=None, pack=None):
+                 specialize=None, max_unroll=None, pack=None, persistent=None, peer_push=False):
         self.program, self.ops, self.ana, self.geo = program, ops, ana, geo
         self.specialize = specialize or {}
         self.ct = ana.dtype
@@ -550,6 +561,18 @@ class StreamKernelGen:
         self.fast_path = os.environ.get("SFB200_FASTPATH", "1") != "0"
         self.with_bc = True
         self._tmp = 0
+        # how produced planes get their out-of-domain cells set to the boundary value (see _finish_field)
+        self.bc_mode = os.environ.get("SFB200_BC_MODE", "thread")
+        if self.bc_mode not in ("thread", "cta"):
+            self.bc_mode = "thread"
+        # persistent scheduling (see schedule_work): tiles of the in-plane grid
+        self.persistent = persistent_default() if persistent is None else bool(persistent)
+        # slab mode: the kernel stores the edge planes of its results a second time, straight into the
+        # neighbouring GPUs' halo planes (peer stores over NVLink), instead of leaving them to a copy
+        self.peer_push = bool(peer_push)
+        gx = -(-self.NK // geo.BK)
+        gy = -(-self.NJ // geo.BJ) if ana.ndim == 3 else 1
+        self.n_tiles = gx * gy
 
     # ------------------------------------------------------------------ unrolling
     def _choose_unroll(self, cap):
@@ -638,9 +661,20 @@ class StreamKernelGen:
         self.sc_name = {s: "s{}".format(n) for n, s in enumerate(self.scalars)}
         params += ["const {} {}".format(ctype_of(self.program.fields[s].data_type), self.sc_name[s])
                    for s in self.scalars]
-        params += ["const int s_base", "const int s_begin", "const int s_end", "const int chunk"]
+        params += ["const int s_base", "const int s_begin", "const int s_end"]
+        params += ["int* __restrict__ work_tab"] if self.persistent else ["const int chunk"]
+        if self.peer_push:
+            # per stored field: byte distance from a cell of this rank's buffer to the same cell of the
+            # lower / upper neighbour's buffer, and the planes that go there (< lo_end, >= hi_begin)
+            for n in range(len(stored)):
+                params += ["const i64 pd_lo_{}".format(n), "const i64 pd_hi_{}".format(n),
+                           "const int pe_lo_{}".format(n), "const int pb_hi_{}".format(n)]
         self.fid = {name: "f{}".format(n) for n, name in enumerate(a.fields)}
+        static_d = self.static(g.D)
+        if g.direct and not static_d:
+            raise NotStreamable("direct input rows need a TMA ring whose depth divides the unroll factor")
 
+        # ---- once per CTA: thread coordinates, shared memory, barriers, register windows
         e("extern __shared__ __align__(1024) unsigned char sf_smem[];")
         if g.KS == 32:
             e("const int lane = threadIdx.x & 31;")
@@ -651,16 +685,77 @@ class StreamKernelGen:
         e("const int wr = warp / {};".format(g.WC))
         e("const int wc = warp % {};".format(g.WC))
         e("(void)wr; (void)wc;")
-        e("const int tile_k0 = blockIdx.x * {};".format(g.BK))
-        if ndim == 3:
-            e("const int tile_j0 = blockIdx.y * {};".format(g.BJ))
-        e("const int c_begin = s_begin + blockIdx.z * chunk;")
-        e("const int c_end = min(c_begin + chunk, s_end);")
-        e("if (c_begin >= c_end) return;")
         e("const int c0 = (wc * {} + lane) * {};            // first owned column inside the tile".format(g.KS, V))
-        e("const int gk = tile_k0 - {} + c0;                 // its global k".format(g.HK0))
         if ndim == 3:
             e("const int r0 = wr * {};".format(R))
+        for n, i in enumerate(ext):
+            e("{T}* const tile_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
+                T=T, f=self.fid[i.name], o=g.tile_off[i.name]))
+        for i in a.fields.values():
+            if i.row_ring and i.name not in g.direct:
+                e("{T}* const xrow_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
+                    T=T, f=self.fid[i.name], o=g.xrow_off[i.name]))
+            if i.col_ring:
+                e("{T}* const xcol_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
+                    T=T, f=self.fid[i.name], o=g.xcol_off[i.name]))
+        e("unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.bar_off))
+        e("if (threadIdx.x == 0) {")
+        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D * (g.NW if g.pair else 1)), 2)
+        e("sf_fence_barrier_init();", 2)
+        e("}")
+        e("__syncthreads();")
+        zero = "make_float2(0.0f, 0.0f)" if self.G == 2 else self.lit(0)
+        for i in a.fields.values():
+            if i.consumed:
+                W = self.wperiod(i) or i.window
+                e("{ET} w_{f}[{W}][{R}][{VH}];".format(ET=self.ET, f=self.fid[i.name], W=W, R=R, VH=self.VH))
+                e("#pragma unroll")
+                e("for (int a = 0; a < {}; ++a)".format(W))
+                e("#pragma unroll", 2)
+                e("for (int r = 0; r < {}; ++r)".format(R), 2)
+                e("#pragma unroll", 3)
+                e("for (int v = 0; v < {}; ++v) w_{}[a][r][v] = {};".format(self.VH, self.fid[i.name], zero), 3)
+            if i.row_ring and i.name not in g.direct and not self.static(i.row_ring):
+                e("int xr_{} = 0;".format(self.fid[i.name]))
+            if i.col_ring and not self.static(i.col_ring):
+                e("int xc_{} = 0;".format(self.fid[i.name]))
+        if static_d:
+            e("u32 phase = 0;")
+        else:
+            e("int slot = 0; u32 phase = 0;")
+        e("const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform")
+
+        # ---- the segment(s) this CTA streams: a tile and a range of planes of the streamed dimension
+        gx = -(-self.NK // g.BK)
+        if self.persistent:
+            # persistent CTAs (one per SM slot) fetch work items -- (tile, first plane, end plane),
+            # planes relative to s_begin -- from the list the host scheduled (``schedule_work``): item
+            # blockIdx.x first, then whatever is next on the shared counter.  Items are ordered so
+            # that CTAs running at the same time hold adjacent tiles at the same planes; fetching
+            # dynamically lets CTAs on cheap (interior) tiles take over work from those on domain-edge
+            # tiles, which run the boundary code in every step.
+            e("int* const sf_item = reinterpret_cast<int*>(sf_smem + {});".format(g.item_off))
+            e("int item = blockIdx.x;")
+            e("#pragma unroll 1")
+            e("while (item < __ldg(work_tab + 2)) {")
+            e("const int tile = work_tab[3 + 3 * item];")
+            e("const int p_begin = work_tab[4 + 3 * item];")
+            e("const int p_end = work_tab[5 + 3 * item];")
+            e("const int tile_k0 = (tile % {}) * {};".format(gx, g.BK))
+            if ndim == 3:
+                e("const int tile_j0 = (tile / {}) * {};".format(gx, g.BJ))
+            e("const int c_begin = s_begin + p_begin;")
+            e("const int c_end = s_begin + p_end;")
+        else:
+            e("{")
+            e("const int tile_k0 = blockIdx.x * {};".format(g.BK))
+            if ndim == 3:
+                e("const int tile_j0 = blockIdx.y * {};".format(g.BJ))
+            e("const int c_begin = s_begin + blockIdx.z * chunk;")
+            e("const int c_end = min(c_begin + chunk, s_end);")
+            e("if (c_begin >= c_end) return;")
+        e("const int gk = tile_k0 - {} + c0;                 // global k of the first owned column".format(g.HK0))
+        if ndim == 3:
             e("const int gj0 = tile_j0 - {} + r0;".format(g.HJ0))
         # in-domain mask of the owned cells, store mask of the owned rows
         e("u32 cmask = 0;")
@@ -687,40 +782,7 @@ class StreamKernelGen:
         for n in range(len(stored)):
             e("{T}* ob_{n} = o_{n} + out_off;".format(T=T, n=n))
             e("asm volatile(\"\" : \"+l\"(ob_{n}));".format(n=n))
-        # shared memory carve-up
-        for n, i in enumerate(ext):
-            e("{T}* const tile_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
-                T=T, f=self.fid[i.name], o=g.tile_off[i.name]))
-        for i in a.fields.values():
-            if i.row_ring and i.name not in g.direct:
-                e("{T}* const xrow_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
-                    T=T, f=self.fid[i.name], o=g.xrow_off[i.name]))
-            if i.col_ring:
-                e("{T}* const xcol_{f} = reinterpret_cast<{T}*>(sf_smem + {o});".format(
-                    T=T, f=self.fid[i.name], o=g.xcol_off[i.name]))
-        e("unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.bar_off))
-        e("if (threadIdx.x == 0) {")
-        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D * (g.NW if g.pair else 1)), 2)
-        e("sf_fence_barrier_init();", 2)
-        e("}")
-        e("__syncthreads();")
-        # register windows
-        zero = "make_float2(0.0f, 0.0f)" if self.G == 2 else self.lit(0)
-        for i in a.fields.values():
-            if i.consumed:
-                W = self.wperiod(i) or i.window
-                e("{ET} w_{f}[{W}][{R}][{VH}];".format(ET=self.ET, f=self.fid[i.name], W=W, R=R, VH=self.VH))
-                e("#pragma unroll")
-                e("for (int a = 0; a < {}; ++a)".format(W))
-                e("#pragma unroll", 2)
-                e("for (int r = 0; r < {}; ++r)".format(R), 2)
-                e("#pragma unroll", 3)
-                e("for (int v = 0; v < {}; ++v) w_{}[a][r][v] = {};".format(self.VH, self.fid[i.name], zero), 3)
-            if i.row_ring and i.name not in g.direct and not self.static(i.row_ring):
-                e("int xr_{} = 0;".format(self.fid[i.name]))
-            if i.col_ring and not self.static(i.col_ring):
-                e("int xc_{} = 0;".format(self.fid[i.name]))
-        # lower-dimensional inputs that do not vary along the streamed dimension: loaded once
+        # lower-dimensional inputs that do not vary along the streamed dimension: loaded once per tile
         self.aux_regs = {}
         for n, (field, off) in enumerate(a.aux_hoisted()):
             self.aux_regs[(field, off)] = self._emit_aux_load(field, off, None, "ax{}".format(n), 1)
@@ -733,13 +795,6 @@ class StreamKernelGen:
                 off=a.t_begin_offset(), Um1=U - 1, U=U))
         else:
             e("const int t_begin = c_begin + ({});".format(a.t_begin_offset()))
-        static_d = self.static(g.D)
-        if g.direct and not static_d:
-            raise NotStreamable("direct input rows need a TMA ring whose depth divides the unroll factor")
-        if static_d:
-            e("u32 phase = 0;")
-        else:
-            e("int slot = 0; u32 phase = 0;")
         # TMA issue helper as a lambda
         nbox = g.TC // g.box_cols
         nwarps = g.NT // 32
@@ -747,7 +802,6 @@ class StreamKernelGen:
         # one elected lane of warp 0 arms the mbarrier; with many boxes per plane (wide 2-D tiles) the
         # copies themselves are issued by the first `issuers` warps, one box each per round
         issuers = 1 if total_boxes <= 2 else min(nwarps, nbox)
-        e("const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform")
         if g.pair:
             # every warp stages its own rows (3-D) / columns (2-D) of the plane and owns the barriers
             box_elems = g.box[0] * g.box[1]
@@ -792,7 +846,11 @@ class StreamKernelGen:
             e("};")
         e("const bool issuer = warp_u < {};".format(issuers))
         e("if (issuer && sf_elect_one()) {")
-        e("for (int p = 0; p < {}; ++p) if (t_begin + p < t_end) issue(t_begin + p, p);".format(g.P), 2)
+        if static_d:
+            e("for (int p = 0; p < {}; ++p) if (t_begin + p < t_end) issue(t_begin + p, p);".format(g.P), 2)
+        else:
+            e("for (int p = 0; p < {P}; ++p) if (t_begin + p < t_end) issue(t_begin + p, (slot + p) % {D});".format(
+                P=g.P, D=g.D), 2)
         e("}")
         e("#pragma unroll 1")
         e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
@@ -816,6 +874,18 @@ class StreamKernelGen:
         if static_d and (U // g.D) % 2 == 1:
             e("phase ^= 1u;", 2)
         e("}")
+        if self.persistent:
+            e("__syncthreads();")
+            e("if (threadIdx.x == 0) *sf_item = (int)gridDim.x + atomicAdd(&work_tab[0], 1);")
+            e("__syncthreads();")
+            e("item = *sf_item;")
+        e("}   // segment")
+        if self.persistent:
+            # the last CTA to leave resets the counters for the next launch of this table
+            e("if (threadIdx.x == 0) {")
+            e("__threadfence();", 2)
+            e("if (atomicAdd(&work_tab[1], 1) == (int)gridDim.x - 1) { work_tab[0] = 0; work_tab[1] = 0; __threadfence(); }", 2)
+            e("}")
         body = "\n".join(self.lines)
         digest = hashlib.sha1((body + ";".join(params)).encode()).hexdigest()[:12]
         name = "sf_stream_{}".format(digest)
@@ -825,7 +895,9 @@ class StreamKernelGen:
         args += [("buf", i.name) for i in stored]
         args += [("buf", name) for name in a.aux]
         args += [("scalar", self.program.fields[s].data_type, s) for s in self.scalars]
-        args += [("slab",), ("chunk",)]
+        args += [("slab",), ("worktab",) if self.persistent else ("chunk",)]
+        if self.peer_push:
+            args += [("push", i.name) for i in stored]
         return name, src, args
 
     def _needs_fixup(self, info):
@@ -909,12 +981,28 @@ class StreamKernelGen:
         if self.with_bc and self._needs_fixup(info):
             e("{")
             e("const bool pin = (unsigned)({}) < {}u;".format(plane_expr, self.NS), 3)
-            e("if (!(pin && interior)) {", 3)
+            full = (1 << (R * V)) - 1
+            bc = self.lit(info.bc)
+
+            def fix(r, v, ind):
+                e("{c} = {bc};".format(c=self.cellref("nv[{}]".format(r), v), bc=bc), ind)
+
+            # one in-domain bit per owned cell.  "thread": only warps that own cells outside the domain
+            # (or a plane outside it) enter, and a thread whose cells are all outside overwrites them
+            # without testing each one; "cta": every warp of a tile that has any such cell does
+            cond = "cmask == {}u".format(full) if self.bc_mode == "thread" else "interior"
+            e("if (!(pin && {})) {{".format(cond), 3)
             e("const u32 m = pin ? cmask : 0u;", 4)
+            e("if (m == 0u) {", 4)
+            for r in range(R):
+                for v in range(V):
+                    fix(r, v, 5)
+            e("} else {", 4)
             for r in range(R):
                 for v in range(V):
                     e("if (!((m >> {b}) & 1u)) {c} = {bc};".format(
-                        b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=self.lit(info.bc)), 4)
+                        b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=bc), 5)
+            e("}", 4)
             e("}", 3)
             e("}")
         if info.row_ring and info.name not in g.direct:
@@ -1162,7 +1250,20 @@ class StreamKernelGen:
             e("asm volatile(\"\" : \"+l\"(op));              // one address computation for all rows", 3)
             e("const bool inchunk = ({p}) >= c_begin && ({p}) < c_end;".format(p=plane), 3)
             for r in range(R):
-                e("sf_stg_if(inchunk && (smask & {m}u), op + {o}, nv[{r}]);".format(m=1 << r, o=r * self.NK, r=r), 3)
+                e("sf_stg_if(inchunk && ({sm} & {m}u), op + {o}, nv[{r}]);".format(
+                    sm="smask", m=1 << r, o=r * self.NK, r=r), 3)
+            if self.peer_push:
+                # the few planes next to a slab boundary also go to the neighbour that reads them as halo
+                e("if (inchunk && (({p}) < pe_lo_{n} || ({p}) >= pb_hi_{n})) {{".format(p=plane, n=idx), 3)
+                for side, cond in (("lo", "({p}) < pe_lo_{n}"), ("hi", "({p}) >= pb_hi_{n}")):
+                    e("if ({}) {{".format(cond.format(p=plane, n=idx)), 4)
+                    e("{T}* pp = reinterpret_cast<{T}*>(reinterpret_cast<char*>(op) + pd_{s}_{n});".format(
+                        T=T, s=side, n=idx), 5)
+                    for r in range(R):
+                        e("sf_stg_if(({sm} & {m}u) != 0u, pp + {o}, nv[{r}]);".format(
+                            sm="smask", m=1 << r, o=r * self.NK, r=r), 5)
+                    e("}", 4)
+                e("}", 3)
         self._finish_field(info, plane, u)
         e("}", 2)
 
@@ -1648,13 +1749,77 @@ def choose_chunk(n_stream, tiles, overhead, sms=148):
     return best[1]
 
 
+EDGE_SLOWDOWN = 0.25        # how much longer a domain-edge tile may take than an interior one (boundary code)
+
+
+def schedule_work(n_tiles, n_planes, slots, overhead):
+    """Work items of a streamed pass for its persistent CTAs: ``[(tile, p_begin, p_end), ...]``, planes
+    relative to the first plane of the slab, in the order the CTAs fetch them (CTA b starts with item
+    b, every CTA then takes the next unclaimed one).
+
+    Two things make a pass fast.  (1) The CTAs running at any moment should work on *adjacent tiles at
+    (nearly) the same planes*: the halo two neighbouring tiles both read then comes from L2 instead of
+    HBM and DRAM pages are used whole -- cutting the (tile, plane) space into ``slots`` equal linear
+    shares, every CTA somewhere else, was measured 43 % slower on the Jacobi-3D chain.
+    (2) Every CTA should stop at the same time although tiles differ in speed (domain-edge tiles run
+    the boundary code in every step).  So the list is
+
+    * whole tiles first, in waves of ``slots`` neighbours that stream in lockstep and pay the warm-up
+      planes once per tile -- as many waves as leave enough other work to even out the differences the
+      whole tiles produce (``EDGE_SLOWDOWN`` per wave);
+    * then the remaining tiles in rounds of plane ranges that halve from round to round (factoring
+      self-scheduling): each round hands about half of what is left to ``slots`` items of equal length,
+      tile-minor so that the CTAs of a round hold adjacent tiles of one range; the last items are short
+      (a few times the warm-up), which bounds how far apart the CTAs finish."""
+    whole = int((n_tiles / float(slots)) / (1.0 + EDGE_SLOWDOWN)) * slots
+    items = [(t, 0, n_planes) for t in range(whole)]
+    tiles = n_tiles - whole
+    if tiles:
+        pieces = max(1, int(round(slots / float(tiles))))          # ranges per tile and round
+        floor_ = max(4 * overhead, 16)                               # shortest range worth a warm-up
+        pos = 0
+        share = 1.0 / (1.0 + EDGE_SLOWDOWN) if not whole else 0.5    # first round: all but the slack
+        while pos < n_planes:
+            rest = n_planes - pos
+            size = max(floor_, -(-int(rest * share) // pieces))
+            share = 0.5
+            if rest - pieces * size < floor_:                        # last round: no stub shorter than the floor
+                k = max(1, min(pieces, rest // floor_))
+                size = -(-rest // k)
+            else:
+                k = pieces
+            for c in range(k):
+                b, e_ = pos + c * size, min(n_planes, pos + (c + 1) * size)
+                if b < e_:
+                    items.extend((whole + t, b, e_) for t in range(tiles))
+            pos += k * size
+    # few tiles, short slab: plain equal ranges sized for whole waves use the slots better
+    ctas = min(slots, len(items))
+    steps = [e_ - b + overhead for (_, b, e_) in items]
+    cost = max(sum(steps) / float(ctas), max(steps)) + min(steps)
+    ci = choose_chunk(n_planes, n_tiles, overhead, sms=slots)
+    nchunk = -(-n_planes // ci)
+    if -(-n_tiles * nchunk // slots) * (ci + overhead) < cost:
+        return [(t, c * ci, min(n_planes, (c + 1) * ci)) for c in range(nchunk) for t in range(n_tiles)]
+    return items
+
+
+def pack_work_table(items):
+    """int32 table the kernel reads and updates: [next-item counter, finished-CTA counter, number of
+    items], then 3 ints per item.  Both counters are zero between launches (the last CTA resets them)."""
+    flat = [0, 0, len(items)]
+    for item in items:
+        flat.extend(item)
+    return flat
+
+
 def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, specialize=None):
     program = lowered.program
     chosen = choose_geometry(program, ops, options)
     if chosen is None:
         raise NotStreamable("group cannot stream")
     ana, geo = chosen
-    gen = StreamKernelGen(program, ops, ana, geo, specialize)
+    gen = StreamKernelGen(program, ops, ana, geo, specialize, peer_push=bool(getattr(options, "peer_push", 0)))
     name, src, args = gen.generate()
     if name not in lowered.kernels:
         lowered.kernels[name] = KernelSpec(name, src, (geo.NT, 1, 1), "streamed")
@@ -1671,9 +1836,22 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
     def chunk_for(b, e_):
         if options.chunk:
             return options.chunk
-        return choose_chunk(max(1, e_ - b), gx * gy, overhead, sms=148 * resident)
+        return choose_chunk(max(1, e_ - b), gx * gy, overhead, sms=SM_COUNT * resident)
 
-    def grid(b, e_):
+    def work_items(b, e_, resident_ctas=None):
+        """Work items of the persistent CTAs for planes [b, e_): one CTA per slot the device really
+        offers (``resident_ctas`` = occupancy of the loaded function x SMs, supplied by the executor;
+        the estimate otherwise)."""
+        slots = resident_ctas or SM_COUNT * resident
+        return schedule_work(gx * gy, max(1, e_ - b), slots, overhead)
+
+    def work_table(b, e_, resident_ctas=None):
+        return pack_work_table(work_items(b, e_, resident_ctas))
+
+    def grid(b, e_, resident_ctas=None):
+        if gen.persistent:
+            slots = resident_ctas or SM_COUNT * resident
+            return (min(slots, len(work_items(b, e_, resident_ctas))), 1, 1)
         ci = chunk_for(b, e_)
         return (gx, gy, max(1, -(-(e_ - b) // ci)))
 
@@ -1687,7 +1865,8 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                         info={"V": geo.V, "R": geo.R, "warps": [geo.WR, geo.WC], "threads_per_row": geo.KS,
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
-                              "prefetch": geo.P, "sync": "pair" if geo.pair else "cta", "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "prefetch": geo.P, "persistent": gen.persistent, "peer_push": gen.peer_push,
+                              "tiles": gx * gy, "sync": "pair" if geo.pair else "cta", "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "register_estimate": ana.register_estimate(geo.R, geo.V),
@@ -1696,7 +1875,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                               "reach": reach,
                               "tile_efficiency": _tile_efficiency(ana, geo),
                               "fwd": ana.max_lag,
-                              "chunk_fn": chunk_for})
+                              "chunk_fn": chunk_for, "work_fn": work_table, "work_items_fn": work_items})
     lowered.launches.append(launch)
     lowered.uses_stream = True
     return launch

@@ -98,7 +98,7 @@ class PlanOptions:
              "SFB200_VEC", "SFB200_KS", "SFB200_SYNC", "SFB200_DIRECT")
 
     def __init__(self, fuse=None, max_depth=None, rows_per_thread=None, warps=None, chunk=None,
-                 prefetch=None, vector=None, threads_per_row=None, sync=None, direct=None):
+                 prefetch=None, vector=None, threads_per_row=None, sync=None, direct=None, peer_push=None):
         env = os.environ
         self.is_default = (all(v is None for v in (fuse, max_depth, rows_per_thread, warps, chunk, prefetch, vector,
                                                    threads_per_row, sync, direct))
@@ -115,6 +115,10 @@ class PlanOptions:
         # 1: neighbour rows of a streamed *input* field are read straight from its TMA ring (which then
         # keeps a plane one step longer) instead of being re-published through an exchange ring
         self.direct = int(env.get("SFB200_DIRECT", "0")) if direct is None else int(direct)
+        # slab mode (set by distributed.SlabProgram): streamed kernels store the edge planes of their
+        # results straight into the neighbouring GPUs' halo planes.  Not a tuning knob: it does not
+        # take part in ``is_default`` and survives the replacement of the options by a measured plan.
+        self.peer_push = bool(peer_push)
 
     def as_dict(self):
         return {k: v for k, v in self.__dict__.items() if k != "is_default"}
@@ -217,7 +221,7 @@ def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
     if options.is_default:
         entry = lookup_tuned(program)
         if entry:
-            options = PlanOptions(**entry["options"])
+            options = PlanOptions(**dict(entry["options"], peer_push=options.peer_push))
             tuned_from = entry.get("measured")
     lowered = lower_cuda.LoweredProgram(program)
     passes = []

@@ -442,3 +442,52 @@ def test_pair_sync_bit_identical_at_scale(gpu, kind):
         sums.append(p.rt.checksum(p.buffers[out].dptr, n, dt))
         p.close()
     assert sums[1][1] == sums[0][1] and sums[2][1] == sums[0][1], sums
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "hdiff_24x28x16", "fork_join_20x16x24",
+                                  "jacobi2d_96x128_6itr_shrink_f64", "lowdim3d_20x24x48_3st_f32"])
+def test_chunk_grid_still_matches_oracle(gpu, name, monkeypatch):
+    """SFB200_PERSISTENT=0: the one-CTA-per-(tile, chunk) grid the persistent schedule replaced."""
+    from oracle import reference_numpy as rn
+    monkeypatch.setenv("SFB200_PERSISTENT", "0")
+    inputs = random_inputs(name, seed=13)
+    expected = rn.run_reference(program_path(name), inputs)
+    got, prog = _run_cuda(name, inputs)
+    assert not any(l.info.get("persistent") for l in prog.lowered.launches)
+    _check(name, got, expected)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["jacobi3d", "jacobi2d", "hdiff"])
+def test_persistent_schedule_bit_identical_at_scale(gpu, kind, monkeypatch):
+    """Persistent CTAs stream several (tile, plane-range) segments each, re-entering the pipeline at every
+    segment; the result must equal the chunk grid's and the one-operator kernels' bit for bit, and the
+    work table must have used every slot of the device."""
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    if kind == "jacobi3d":
+        prog, out, dt, fills = programs.jacobi3d_chain([320, 448, 512], 8), "b7", np.float32, {"a": (0.0, 1.0)}
+    elif kind == "jacobi2d":
+        prog, out, dt, fills = programs.jacobi2d_chain([3000, 16384], 8), "b7", np.float64, {"a": (0.0, 1.0)}
+    else:
+        prog, out, dt = programs.hdiff([192, 256, 80]), "out", np.float32
+        fills = {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)}
+    path = programs.write_program(prog, "persist_" + kind)
+    n = int(np.prod(prog["dimensions"]))
+    sums = []
+    for mode, opts in (("1", None), ("0", None), ("1", PlanOptions(fuse=False))):
+        monkeypatch.setenv("SFB200_PERSISTENT", mode)
+        p = CudaProgram(path, plan_options=opts)
+        for k, (name, (lo, hi)) in enumerate(sorted(fills.items())):
+            p.rt.fill_hash(p.buffers[name].dptr, n, dt, seed=99 + k, lo=lo, hi=hi)
+        for _ in range(2):
+            p.execute()
+        p.rt.stream_synchronize()
+        sums.append(p.rt.checksum(p.buffers[out].dptr, n, dt))
+        if mode == "1" and opts is None:
+            l, fn, grid, pack = p._packs[0]
+            assert l.info["persistent"] and 0.9 * p._resident_ctas(l) <= grid[0] <= p._resident_ctas(l) and grid[1:] == (1, 1)
+        p.close()
+    assert sums[1][1] == sums[0][1] and sums[2][1] == sums[0][1], sums

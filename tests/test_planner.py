@@ -26,8 +26,25 @@ def test_config1_plan(native_lib):
     info = launches[0].info
     assert info["tile"] == [72, 64] and info["R"] == 3 and info["prefetch"] == 5 and info["unroll"] == 6
     assert launches[0].block == (384, 1, 1) and launches[0].smem <= 227 * 1024
-    gx, gy, gz = launches[0].grid_fn(0, 1024)
-    assert (gx, gy) == (19, 16) and gx * gy * gz >= 4 * 148
+    # persistent CTAs, one per SM, fetching items from a shared list: one wave of whole tiles (neighbours in
+    # lockstep), then the other 156 tiles in rounds of plane ranges that halve -- 512, 256, ... 32 -- so that
+    # the CTAs finish together although domain-edge tiles are slower
+    assert info["persistent"] and info["tiles"] == 19 * 16
+    assert launches[0].grid_fn(0, 1024) == (148, 1, 1)
+    items = info["work_items_fn"](0, 1024)
+    assert items[:148] == [(t, 0, 1024) for t in range(148)]
+    rest = items[148:]
+    assert {t for t, _, _ in rest} == set(range(148, 304))
+    assert rest[:156] == [(t, 0, 512) for t in range(148, 304)]          # tile-minor: neighbours side by side
+    lengths = [p1 - p0 for _, p0, p1 in rest]
+    assert lengths == sorted(lengths, reverse=True) and lengths[-1] == 32
+    for t in range(148, 304):
+        covered = sorted((p0, p1) for tt, p0, p1 in rest if tt == t)
+        assert covered[0][0] == 0 and covered[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    steps = sum(p1 - p0 + info["stream_overhead_planes"] for _, p0, p1 in items) / 148.0
+    assert steps <= 1.03 * (19 * 16 * 1024 / 148.0)
+    table = info["work_fn"](0, 1024)
+    assert table[:3] == [0, 0, len(items)] and table[3:9] == [0, 0, 1024, 1, 0, 1024]
     # algorithmic bytes of a pass: the field in, the field out
     assert launches[0].reads == ["a"] and launches[0].writes == ["b3"]
 
@@ -38,13 +55,55 @@ def test_config3_plan_uses_small_independent_ctas(native_lib):
     assert [len(l.ops) for l in launches] == [8, 8]
     l = launches[0]
     assert l.block == (64, 1, 1) and l.info["tile"] == [1, 256] and l.info["prefetch"] == 5
-    # four 2-warp CTAs share an SM (255 registers each): the chunking fills 4 x 148 slots several times over
-    gx, gy, gz = l.grid_fn(0, 32768)
-    assert gx == 137 and gy == 1
-    waves = gx * gz / (4 * 148.0)
-    assert waves >= 4 and (waves - int(waves) > 0.85 or waves == int(waves))
+    # four 2-warp CTAs share an SM (255 registers each): fewer tiles (137) than slots (592), so every tile is
+    # cut into row ranges -- four long ones first, then ever shorter ones; warm-up rows stay a small part
+    assert l.info["tiles"] == 137
+    items = l.info["work_items_fn"](0, 32768, 4 * 148)
+    assert l.grid_fn(0, 32768, 4 * 148) == (4 * 148, 1, 1) and len(items) >= 4 * 4 * 148
+    assert [t for t, _, _ in items[:137]] == list(range(137))          # tile-minor: neighbours side by side
+    rows = sorted((p0, p1) for (t, p0, p1) in items if t == 5)
+    assert rows[0][0] == 0 and rows[-1][1] == 32768 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
     overhead = l.info["stream_overhead_planes"]
-    assert overhead * gz <= 0.03 * 32768
+    assert overhead * len(rows) <= 0.03 * 32768
+    assert min(p1 - p0 for p0, p1 in rows) >= 4 * overhead
+
+
+def test_one_cta_per_tile_chunk_grid_still_available(native_lib, monkeypatch):
+    monkeypatch.setenv("SFB200_PERSISTENT", "0")
+    p, prog = _program(1)
+    l = p.lowered.launches[0]
+    assert not l.info["persistent"] and ("chunk",) in l.args
+    gx, gy, gz = l.grid_fn(0, 1024)
+    assert (gx, gy) == (19, 16) and gx * gy * gz >= 4 * 148
+
+
+def test_schedule_work_covers_every_plane_once():
+    from stencilflow_b200.lower_stream import schedule_work, pack_work_table
+    for (tiles, planes, slots, ov) in [(304, 1024, 148, 8), (1184, 256, 148, 8), (150, 1024, 148, 8), (1, 32, 148, 8),
+                                       (24, 1024, 148, 5), (137, 32768, 592, 16), (3, 7, 148, 2), (600, 64, 148, 8),
+                                       (304, 64, 148, 8), (2, 1024, 148, 8), (1184, 2048, 148, 8)]:
+        items = schedule_work(tiles, planes, slots, ov)
+        seen = {}
+        for (t, p0, p1) in items:
+            assert 0 <= t < tiles and 0 <= p0 < p1 <= planes
+            seen.setdefault(t, []).append((p0, p1))
+        assert sorted(seen) == list(range(tiles))
+        for t, ranges in seen.items():
+            ranges.sort()
+            assert ranges[0][0] == 0 and ranges[-1][1] == planes
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        # longest items first: what is fetched late is short
+        lengths = [p1 - p0 for _, p0, p1 in items]
+        assert lengths[0] == max(lengths)
+        # the warm-up planes every item re-streams stay a small part of a big pass
+        if tiles * planes >= 64 * slots * ov:
+            assert sum(p1 - p0 + ov for _, p0, p1 in items) <= 1.06 * tiles * planes
+        table = pack_work_table(items)
+        assert table[:3] == [0, 0, len(items)] and len(table) == 3 + 3 * len(items)
+    # exactly 8 tiles per SM (config 4 on 8 GPUs): whole tiles only, nothing is cut
+    assert schedule_work(1184, 256, 148, 8) == [(t, 0, 256) for t in range(1184)]
+    # a tiny grid is cut as finely as its single tile allows: launch latency, not warm-up, is what counts
+    assert len(schedule_work(1, 32, 148, 8)) == 32
 
 
 def test_cost_model_picks_small_ctas_and_depth_for_untuned_2d(native_lib):
