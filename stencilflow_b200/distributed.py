@@ -125,29 +125,14 @@ def total_reach(lowered):
     return max(need_back, need_fwd)
 
 
-def halo_schedule(lowered, slab: Slab) -> List[HaloSend]:
-    """Which planes this rank must push to which neighbour after which launch.
+def halo_schedule(lowered, slab: Slab) -> List["HaloSend"]:
+    """Which planes this rank must push to which neighbour after which launch (``ExchangePlan.for_rank``).
 
     Field F written by launch l and read by a later launch with reach (back, fwd) along the slab
     axis: the upper neighbour needs my top ``back`` planes as its lower halo, the lower neighbour my
     bottom ``fwd`` planes as its upper halo.  Program inputs are loaded with their halos and never
     exchanged."""
-    sends = []
-    if lowered.slab_axis is None or slab.world == 1:
-        return sends
-    n_launch = len(lowered.launches)
-    for idx, l in enumerate(lowered.launches):
-        for field in l.writes:
-            back = fwd = 0
-            for later in range(idx + 1, n_launch):
-                r = launch_reach(lowered, later).get(field)
-                if r:
-                    back, fwd = max(back, r[0]), max(fwd, r[1])
-            if back and slab.rank + 1 < slab.world:
-                sends.append(HaloSend(idx, field, slab.rank + 1, slab.end - back, slab.end))
-            if fwd and slab.rank > 0:
-                sends.append(HaloSend(idx, field, slab.rank - 1, slab.begin, slab.begin + fwd))
-    return sends
+    return ExchangePlan(lowered).for_rank(slab)
 
 
 class ExchangePlan:

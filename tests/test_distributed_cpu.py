@@ -48,6 +48,8 @@ def _run_world(path, fuse, world=2, seed=5):
     ("box3d_10x12x16", False),
     ("lowdim3d_20x24x48_3st_f32", True),
     ("ref_varying_dimensionality", True),
+    ("upwind3d_fwd_24x16x32_4st", False),          # one-sided reach: rank 0 only receives
+    ("upwind3d_bwd_20x12x32_5st_f64", True),
 ])
 def test_two_ranks_reproduce_single_domain(native_lib, name, fuse):
     results = _run_world(program_path(name), fuse)

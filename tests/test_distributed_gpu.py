@@ -20,6 +20,21 @@ def _gpu_count(native_lib):
     return n.value
 
 
+def _run_group(cmd, env, timeout):
+    """Runs ``cmd`` in its own process group and kills the whole group on a timeout, so that a hung
+    rank cannot keep a GPU busy behind the test's back."""
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                            start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+        return out, proc.returncode
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, _ = proc.communicate()
+        return (out or "") + "\n[timeout after {} s: process group killed]".format(timeout), -9
+
+
 @pytest.mark.parametrize("name,fuse", [
     ("ref_jacobi3d_32x32x32_8itr_8vec", True),
     ("ref_jacobi3d_32x32x32_8itr_8vec", False),
@@ -29,6 +44,12 @@ def _gpu_count(native_lib):
     ("lowdim3d_20x24x48_3st_f32", True),
     ("ref_varying_dimensionality", True),
     ("chain3d:160x64x128", True),
+    ("upwind3d_fwd_24x16x32_4st", True),           # one-sided reach: rank 0 only receives, rank 1 only sends
+    ("upwind3d_fwd_24x16x32_4st", False),
+    ("upwind3d_bwd_20x12x32_5st_f64", True),
+    ("ref_jacobi3d_32x32x32_8itr_8vec:copy", True),    # SFB200_PEER_PUSH=0: copy pushes for streamed passes too
+    ("upwind3d_fwd_24x16x32_4st:copy", True),
+    ("chain3d:160x64x128:d2", True),                    # 4 passes, ping-pong storage, in-kernel pushes
 ])
 def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if _gpu_count(native_lib) < 2:
@@ -41,12 +62,24 @@ def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py"), name, "1" if fuse else "0"]
     env = dict(os.environ)
+    if name.endswith(":copy"):
+        name = name[:-len(":copy")]
+        env["SFB200_PEER_PUSH"] = "0"
+    if name.endswith(":d2"):
+        name = name[:-len(":d2")]
+        env["SFB200_MAX_DEPTH"] = "2"
+    if name.startswith("upwind3d") and fuse:
+        env["SFB200_MAX_DEPTH"] = "2"               # two passes: the one-sided halo really is exchanged
+    cmd[-2] = name
     if name.startswith("chain3d"):
         env["SFB200_PIPELINE_PIECES"] = "4"         # 88 planes per rank: pieces of 22 planes
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
-    assert res.returncode == 0, res.stdout[-4000:]
-    lines = [json.loads(l[len("RESULT "):]) for l in res.stdout.splitlines() if l.startswith("RESULT ")]
+    out, code = _run_group(cmd, env, 240)
+    assert code == 0, out[-4000:]
+    lines = [json.loads(l[len("RESULT "):]) for l in out.splitlines() if l.startswith("RESULT ")]
     assert len(lines) == 2 and all(l["ok"] for l in lines)
-    if name.startswith("chain3d"):
+    if name.startswith("chain3d") and "SFB200_MAX_DEPTH" not in env:
         # wide halo (accumulated reach 8) -> the host-array call ran as the overlapped exchange-free schedule
         assert all(l["halo"] == 8 and l["report"]["call_pipelined"] for l in lines), lines
+    if name.startswith("upwind3d"):
+        assert sorted(l["sends"] for l in lines) != [0, 0]          # the halo really was exchanged
+        assert min(l["sends"] for l in lines) == 0                  # ... by one side only

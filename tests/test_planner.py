@@ -49,7 +49,18 @@ def test_config1_plan(native_lib):
     assert launches[0].reads == ["a"] and launches[0].writes == ["b3"]
 
 
-def test_config3_plan_uses_small_independent_ctas(native_lib):
+def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
+    p, prog = _program(3)
+    # 137 column tiles on 4 x 148 CTA slots: fewer tiles than slots, so the plain (tile, chunk) grid is used
+    l = p.lowered.launches[0]
+    assert not l.info["persistent"]
+    gx, gy, gz = l.grid_fn(0, 32768)
+    assert gx == 137 and gy == 1
+    waves = gx * gz / (4 * 148.0)
+    assert waves >= 4 and (waves - int(waves) > 0.85 or waves == int(waves))
+    assert l.info["stream_overhead_planes"] * gz <= 0.03 * 32768
+    # ... unless persistent CTAs are forced
+    monkeypatch.setenv("SFB200_PERSISTENT", "1")
     p, prog = _program(3)
     launches = p.lowered.launches
     assert [len(l.ops) for l in launches] == [8, 8]
