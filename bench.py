@@ -7,7 +7,12 @@ A *step* is one execution of the whole stencil program (all chained operators) o
 field.  Default workload = BASELINE.json configs[1]: Jacobi-3D, 8 chained operators, 1024^3 float32,
 constant boundary.  For N > 1 (launched by torchrun, one rank per GPU) every rank owns a 1024^3 slab
 of a (N*1024) x 1024 x 1024 domain and exchanges halos with its neighbours over NVLink once per
-fused pass (weak scaling).
+fused pass (weak scaling).  The same line also carries
+
+* ``verify``: the timed result checked -- against the CPU oracle on a block of planes, against the
+  one-operator kernels at full size, and (N > 1) bit for bit against one GPU running the whole domain;
+* ``strong``: BASELINE.json configs[4] (Jacobi-3D 2048^3 x 64 operators) split over the same N GPUs,
+  with the one-GPU time of the same box next to it.
 
 One JSON line is printed by rank 0; see DESIGN.md section "Measurement" for the definition of every key.
 """
@@ -17,7 +22,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -104,9 +108,10 @@ def build_config(index, scale_i=1):
 
 
 INPUT_RANGES = {"inp": (1.0, 2.0), "coeff": (0.0, 0.05), "w": (0.9, 1.1)}   # hdiff; everything else U[0,1)
+SEED = 1234
 
 
-def fill_inputs(program, seed=1234, index_offsets=None):
+def fill_inputs(program, seed=SEED, index_offsets=None):
     rt = program.rt
     for k, (name, f) in enumerate(program.program.fields.items()):
         if f.kind != "input":
@@ -121,99 +126,150 @@ def fill_inputs(program, seed=1234, index_offsets=None):
     rt.stream_synchronize()
 
 
-def cpu_reference_rate(index, target_seconds=12.0, threads=None):
-    """Times the CPU restatement of the reference program (oracle/reference_cpp.py: OpenMP over the
-    outermost loop, -O3 -march=native -ffast-math, all transients live) on a bounded sample of the
-    workload.  Returns (cell-updates/s, cores, sample description)."""
-    from oracle import reference_cpp
-    from stencilflow_b200 import programs, synthetic
-    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank);
-    # SFB200_REF_THREADS overrides.  The count reported is the one the OpenMP runtime really uses.
-    cores = threads or int(os.environ.get("SFB200_REF_THREADS", "0")) or os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)
-    name, prog, _ = programs.baseline_config(index, VARIANT)
+def host_inputs(prog, dims, seed=SEED):
+    """The synthetic input fields of ``prog`` restricted to the leading ``dims`` block, generated on
+    the host (same counter hash as ``fill_inputs``: element values depend on the *global* flat index)."""
+    from stencilflow_b200 import synthetic
     full = list(prog["dimensions"])
-    nops = len(prog["program"])
-
-    short = [d < 256 for d in full]                    # hdiff's vertical axis is kept as it is
-
-    def sized(frac):
-        return [d if sh else max(16, int(d * frac) // 8 * 8) for d, sh in zip(full, short)]
-
     iters = ["i", "j", "k"][3 - len(full):]
+    out = {}
+    for k, (name, cfg) in enumerate(prog["inputs"].items()):
+        lo, hi = INPUT_RANGES.get(name, (0.0, 1.0))
+        its = cfg.get("input_dims", iters)
+        if not its:
+            out[name] = np.dtype(cfg["data_type"]).type(0.5)
+            continue
+        fshape = tuple(n for it, n in zip(iters, full) if it in its)
+        bshape = tuple(n for it, n in zip(iters, dims) if it in its)
+        if fshape[1:] != bshape[1:]:
+            raise ValueError("only the outermost dimension may be cut")
+        # a leading block of a row-major field is a prefix of its flat index space
+        out[name] = synthetic.fill_hash(bshape, np.dtype(cfg["data_type"]), seed + k, lo, hi)
+    return out
 
-    used = [cores, 0.0]               # threads the OpenMP runtime uses, seconds of the last timed sample
 
-    def run(dims):
-        p = json.loads(json.dumps(prog))
-        p["dimensions"] = dims
-        ref = reference_cpp.CompiledReference(p)
-        inputs = {}
-        for k, (iname, cfg) in enumerate(p["inputs"].items()):
-            lo, hi = INPUT_RANGES.get(iname, (0.0, 1.0))
-            shape = tuple(n for it, n in zip(iters, dims) if it in cfg.get("input_dims", iters))
-            inputs[iname] = synthetic.fill_hash(shape, np.dtype(cfg["data_type"]), 1234 + k, lo, hi)
-        ref.allocate_transients()
-        used[0] = ref.threads
-        ref(**inputs)                                   # warm (page faults, OpenMP team)
+# ------------------------------------------------------------------------------------ CPU arm
+
+
+class CpuSample:
+    """The reference's CPU program (oracle/reference_cpp.py: OpenMP over the outermost loop, DaCe's flags
+    -O3 -march=native -ffast-math, all transients live) built and allocated once for a bounded sample
+    of a workload; ``run()`` times one execution."""
+
+    def __init__(self, index, target_seconds=10.0, threads=None):
+        from oracle import reference_cpp
+        from stencilflow_b200 import programs, synthetic
+        # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank);
+        # SFB200_REF_THREADS overrides.  The count reported is the one the OpenMP runtime really uses.
+        cores = threads or int(os.environ.get("SFB200_REF_THREADS", "0")) or os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        self.name, prog, _ = programs.baseline_config(index, VARIANT)
+        full = list(prog["dimensions"])
+        self.nops = len(prog["program"])
+        short = [d < 256 for d in full]                    # hdiff's vertical axis is kept as it is
+        iters = ["i", "j", "k"][3 - len(full):]
+
+        def sized(frac):
+            return [d if sh else max(16, int(d * frac) // 8 * 8) for d, sh in zip(full, short)]
+
+        def build(dims):
+            p = json.loads(json.dumps(prog))
+            p["dimensions"] = dims
+            ref = reference_cpp.CompiledReference(p)
+            inputs = {}
+            for k, (iname, cfg) in enumerate(p["inputs"].items()):
+                lo, hi = INPUT_RANGES.get(iname, (0.0, 1.0))
+                shape = tuple(n for it, n in zip(iters, dims) if it in cfg.get("input_dims", iters))
+                inputs[iname] = synthetic.fill_hash(shape, np.dtype(cfg["data_type"]), SEED + k, lo, hi)
+            ref.allocate_transients()
+            return ref, inputs
+
+        # a small probe tells how large a sample fits the time budget (and the host's memory)
+        probe_dims = sized(0.125 if full[0] >= 1024 else 1.0)
+        ref, inputs = build(probe_dims)
+        ref(**inputs)
         t0 = time.perf_counter()
         ref(**inputs)
-        dt = time.perf_counter() - t0
-        used[1] = dt
-        return nops * float(np.prod(dims)) / dt, dt
+        rate = self.nops * float(np.prod(probe_dims)) / (time.perf_counter() - t0)
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 16 << 30
+        itemsize = np.dtype(next(iter(prog["inputs"].values()))["data_type"]).itemsize
+        mem_cells = 0.5 * avail / ((self.nops + 2) * itemsize)
+        cells_full = float(np.prod(full))
+        want_cells = min(cells_full, rate * target_seconds / self.nops, mem_cells)
+        frac = (want_cells / cells_full) ** (1.0 / max(1, short.count(False)))
+        dims = sized(min(1.0, frac))
+        if np.prod(dims) > np.prod(probe_dims):
+            del ref, inputs
+            ref, inputs = build(dims)
+            ref(**inputs)                                   # warm: page faults, OpenMP team
+        else:
+            dims = probe_dims
+        self.ref, self.inputs, self.dims = ref, inputs, dims
+        self.cores = ref.threads
+        self.updates = self.nops * float(np.prod(dims))
 
-    probe_dims = sized(0.125 if full[0] >= 1024 else 1.0)
-    rate, _ = run(probe_dims)
-    cells_full = float(np.prod(full))
-    try:
-        import psutil
-        avail = psutil.virtual_memory().available
-    except Exception:
-        avail = 16 << 30
-    itemsize = np.dtype(next(iter(prog["inputs"].values()))["data_type"]).itemsize
-    mem_cells = 0.5 * avail / ((nops + 2) * itemsize)
-    want_cells = min(cells_full, rate * target_seconds / nops, mem_cells)
-    frac = (want_cells / cells_full) ** (1.0 / max(1, short.count(False)))
-    dims = sized(min(1.0, frac))
-    if np.prod(dims) > np.prod(probe_dims):
-        rate, dt = run(dims)
-    else:
-        dims = probe_dims
-    sample = "{} at {} ({} operators, all transients live), 1 warm + 1 timed execution".format(
-        name, "x".join(map(str, dims)), nops)
-    cpu_reference_rate.last_sample_seconds = used[1]
-    return rate, used[0], sample
+    def run(self):
+        t0 = time.perf_counter()
+        self.ref(**self.inputs)
+        return time.perf_counter() - t0
+
+    def describe(self, timed):
+        return "{} at {} ({} operators, all transients live), 1 warm + {} timed execution{}".format(
+            self.name, "x".join(map(str, self.dims)), self.nops, timed, "" if timed == 1 else "s")
+
+
+def cpu_reference_rate(index, target_seconds=10.0, threads=None):
+    """(cell-updates/s, cores, sample description) of the CPU restatement on a bounded sample."""
+    sample = CpuSample(index, target_seconds, threads)
+    dt = sample.run()
+    return sample.updates / dt, sample.cores, sample.describe(1)
+
+
+def common_config(index, prog, world, scaling):
+    dims = list(prog["dimensions"])
+    fp64 = "float64" in json.dumps(prog["program"])
+    per_gpu = [dims[0] // world] + dims[1:]
+    return {"workload": workload_name(index, prog),
+            "per_gpu": "x".join(map(str, per_gpu)),
+            "l2": "no flush needed: every pass streams fields of {:.1f} GiB, far above the 126 MB L2".format(
+                float(np.prod(per_gpu)) * (8 if fp64 else 4) / 2 ** 30),
+            "input": "U[0,1) counter hash (seed {}), generated in HBM by the GPU arm".format(SEED)}
 
 
 def run_reference_arm(args):
+    """``--impl reference``: the reference's CPU path (the oracle's C++/OpenMP restatement -- the
+    reference itself cannot be built here) on all host cores: built and allocated once,
+    warm executions, then exactly ``--steps`` timed executions of a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rates = []
-    t_all0 = time.perf_counter()
-    cores = os.cpu_count() or 1
-    sample = ""
-    times = []
-    for step in range(args.warmup + args.steps):
-        rate, cores, sample = cpu_reference_rate(args.config, target_seconds=6.0)
-        if step >= args.warmup:
-            rates.append(rate)
-            times.append(cpu_reference_rate.last_sample_seconds)
-        if time.perf_counter() - t_all0 > 150:
-            break
-    value = float(np.mean(rates)) if rates else rate
-    name, prog, _ = build_config(args.config)
-    dims = prog["dimensions"]
+    world = args.gpus
+    steps = max(1, args.steps)
+    # the sample is sized so that warm-up + exactly ``steps`` timed executions take about two minutes
+    sample = CpuSample(args.config, target_seconds=min(8.0, max(0.4, 110.0 / (steps + max(1, args.warmup)))))
+    for _ in range(max(0, args.warmup - 1)):           # CpuSample already ran one warm execution
+        sample.run()
+    times = [sample.run() for _ in range(steps)]
+    dt = float(np.mean(times))
+    value = sample.updates / dt
+    name, prog, _ = build_config(args.config, scale_i=world if args.scaling == "weak" else 1)
+    config = common_config(args.config, prog, world, args.scaling)
+    sample_text = sample.describe(len(times))
+    if world > 1:
+        config["reference_sample"] = sample_text        # the CPU arm times one bounded sample whatever N is
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(rates), "warmup": args.warmup,
-        "ms_per_step": (1e3 * float(np.mean(times)) if times else None),     # one bounded sample (see "sample")
-        "higher_is_better": True,
-        "scaling": args.scaling or "weak", "vs_baseline": None,
-        "dtype": "f64" if "f64" in name else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, prog)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * dt,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64" if "float64" in json.dumps(prog["program"]) else "f32", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": sample.cores, "kind": "port", "sample": sample_text},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
@@ -225,6 +281,203 @@ def workload_name(index, prog):
     kinds = {0: "Jacobi-3D chain", 1: "Jacobi-3D chain", 2: "COSMO hdiff", 3: "Jacobi-2D chain", 4: "Jacobi-3D chain"}
     tag = {"jki": ", layout J,K,I", "w1d": ", x 1-D weight w[k] per stage"}.get(VARIANT, "")
     return "{} {} {}, {} chained operators (BASELINE.json configs[{}]{})".format(kinds[index], dims, dt, nops, index, tag)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+
+def make_program(index, world, rank, local_rank, comm, scaling):
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    name, prog, halo = build_config(index, scale_i=world if scaling == "weak" else 1)
+    path = programs.write_program(prog, name)
+    if world > 1:
+        from stencilflow_b200 import distributed
+        program = distributed.SlabProgram(path, comm, device=local_rank)
+    else:
+        program = CudaProgram(path, device=local_rank)
+    fill_inputs(program, index_offsets=getattr(program, "input_index_offsets", lambda: None)())
+    return name, prog, path, program
+
+
+def time_device(program, steps, warmup, comm, sampler=None):
+    """``steps`` executions bracketed by a barrier + stream synchronisation on both sides, timed with
+    CUDA events on the launch stream.  Returns (ms of this rank, max over ranks, launches)."""
+    rtm = program.rt
+
+    def barrier():
+        rtm.stream_synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    for _ in range(warmup):
+        program.execute()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    launches0 = program.launch_count
+    e0, e1 = rtm.event_create(), rtm.event_create()
+    barrier()
+    rtm.event_record(e0)
+    for _ in range(steps):
+        program.execute()
+    rtm.event_record(e1)
+    rtm.event_synchronize(e1)
+    barrier()
+    ms_local = rtm.elapsed_ms(e0, e1)
+    rtm.event_destroy(e0)
+    rtm.event_destroy(e1)
+    ms = comm.max_float(ms_local) if comm is not None else ms_local
+    return ms_local, ms, program.launch_count - launches0
+
+
+def slab_checksums(program, field, bounds):
+    """Bit checksums of ``field`` per plane range [b, e) of a single-GPU program."""
+    f = program.program.fields[field]
+    plane = int(np.prod(f.shape[1:]))
+    out = []
+    for (b, e) in bounds:
+        out.append(program.rt.checksum(program.buffers[field].dptr + b * plane * f.data_type.bytes,
+                                       (e - b) * plane, f.data_type.type)[1])
+    return out
+
+
+def verify_single(program, prog, path, index, local_rank, planes=128):
+    """Checks the result the timed executions left in HBM (one GPU):
+    ``oracle_block``: the first ``planes`` planes against the CPU oracle (the reference's program
+    restated in C++), run on the leading block of the same synthetic input -- cells whose dependence cone
+    stays inside the block; tolerance 1e-5 (float32) / 1e-12 (float64), BASELINE.json;
+    ``fused_vs_general``: the whole result against the one-operator-per-launch kernels, compared on the
+    device (``sfb_compare``)."""
+    from oracle import reference_cpp, reference_numpy as rn
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    rtm = program.rt
+    fields = program.program.fields
+    out_name = program.program.outputs[0]
+    f_out = fields[out_name]
+    dims = list(prog["dimensions"])
+    nops = len(prog["program"])
+    result = {}
+    # -- CPU oracle on a leading block
+    t0 = time.perf_counter()
+    reach = nops * 2                                  # generous bound on the accumulated extent along i
+    block = min(dims[0], planes + reach)
+    keep = planes if block < dims[0] else dims[0]
+    sub = json.loads(json.dumps(prog))
+    sub["dimensions"] = [block] + dims[1:]
+    ref = reference_cpp.CompiledReference(sub)
+    ins = host_inputs(prog, sub["dimensions"])
+    expected = ref(**ins)[out_name]
+    plane = int(np.prod(f_out.shape[1:]))
+    got = np.empty((keep,) + tuple(f_out.shape[1:]), dtype=f_out.data_type.type)
+    rtm.d2h(got, program.buffers[out_name].dptr, nbytes=keep * plane * f_out.data_type.bytes)
+    rtm.stream_synchronize()
+    halo = {2: 2, 3: 16}.get(index, 0)                # shrink boundaries: junk border excluded (-halo)
+    a, b = expected[:keep], got
+    if halo:
+        # -halo trims every axis (stencilflow/run_program.py:202-209); the block's far side is cut off anyway
+        sl = (slice(halo, None),) + tuple(slice(halo, -halo) for _ in range(a.ndim - 1))
+        a, b = a[sl], b[sl]
+    tol = 1e-12 if f_out.data_type.bytes == 8 else 1e-5
+    err = float(rn.max_relative_error(a, b))
+    result["oracle_block"] = {"planes": int(keep), "cells": int(a.size), "max_rel_err": err, "tolerance": tol,
+                              "ok": bool(err <= tol), "seconds": round(time.perf_counter() - t0, 2)}
+    del expected, got, ins
+    # -- one-operator kernels, full size, compared on the device
+    free_b, _ = rtm.mem_info()
+    need = sum(f.nbytes for f in fields.values() if not f.is_scalar and f.kind != "intermediate") + 2 * f_out.nbytes
+    if free_b > need + (2 << 30):
+        general = CudaProgram(path, device=local_rank, plan_options=PlanOptions(fuse=False))
+        for name, f in fields.items():
+            if f.kind == "input" and not f.is_scalar:
+                rtm.d2d(general.buffers[name].dptr, program.buffers[name].dptr, f.nbytes)
+        general.scalar_values.update(program.scalar_values)
+        general.execute()
+        rtm.stream_synchronize()
+        err, bad = rtm.compare(general.buffers[out_name].dptr, program.buffers[out_name].dptr,
+                               f_out.size, f_out.data_type.type, tol)
+        bits = (rtm.checksum(general.buffers[out_name].dptr, f_out.size, f_out.data_type.type)[1] ==
+                rtm.checksum(program.buffers[out_name].dptr, f_out.size, f_out.data_type.type)[1])
+        result["fused_vs_general"] = {"cells": int(f_out.size), "max_rel_err": float(err), "num_bad": int(bad),
+                                      "bit_identical": bool(bits), "ok": bool(bad == 0)}
+        general.close()
+    else:
+        result["fused_vs_general"] = {"skipped": "not enough free HBM for a second set of fields"}
+    result["ok"] = all(v.get("ok", True) for v in result.values() if isinstance(v, dict))
+    return result
+
+
+def verify_multi(program, prog, path, comm, local_rank):
+    """N > 1: the exchanged slab run against ONE GPU running the whole domain with the same plan
+    (rank 0 does that), owned planes of every rank compared through bit checksums computed on the
+    devices -- halo exchange, storage reuse and counters have to be exactly right for this to match."""
+    from stencilflow_b200.cuda_program import CudaProgram
+    rank = comm.rank
+    out_name = program.program.outputs[0]
+    mine = program.checksum_owned(out_name)[1]
+    bounds = comm.allgather((program.slab.begin, program.slab.end))
+    sums = comm.allgather(mine)
+    result = None
+    if rank == 0:
+        fields = program.program.fields
+        free_b, _ = program.rt.mem_info()
+        need = 4 * max(f.nbytes for f in fields.values() if not f.is_scalar)
+        if free_b > need + (2 << 30):
+            single = CudaProgram(path, device=local_rank)
+            fill_inputs(single)
+            single.execute()
+            single.rt.stream_synchronize()
+            ref = slab_checksums(single, out_name, bounds)
+            single.close()
+            same = [int(a) == int(b) for a, b in zip(ref, sums)]
+            result = {"single_gpu_whole_domain": "x".join(map(str, prog["dimensions"])),
+                      "slabs_bit_identical": same, "ok": bool(all(same))}
+        else:
+            result = {"skipped": "whole domain does not fit one GPU next to the slab", "ok": True}
+    comm.barrier()
+    return result
+
+
+def strong_block(args, world, rank, local_rank, comm, peak_gbs):
+    """BASELINE.json configs[4] -- Jacobi-3D 2048^3 float32, 64 chained operators -- split into slabs
+    over the N GPUs of this run, and on ONE GPU of the same box right after it (rank 0), so that the
+    parallel efficiency t1 / (N * tN) comes from one lease.  The multi-GPU result is compared bit for
+    bit with the one-GPU result (per-slab checksums)."""
+    from stencilflow_b200.cuda_program import CudaProgram
+    steps, warmup = 3, 3
+    name, prog, path, program = make_program(4, world, rank, local_rank, comm, "strong")
+    nops = len(prog["program"])
+    updates = nops * float(np.prod(prog["dimensions"]))
+    ms_local, ms, _ = time_device(program, steps, warmup, comm)
+    out = {"workload": workload_name(4, prog), "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "value": updates / (ms / steps * 1e-3), "unit": UNIT}
+    alg = program.plan.algorithmic_bytes() / world
+    out["roofline_frac"] = alg / (ms_local / steps * 1e-3) / 1e9 / peak_gbs
+    out["launches_per_step"] = program.launches_per_execution
+    if world > 1:
+        out_name = program.program.outputs[0]
+        # checksums of the state after exactly warmup + steps executions
+        mine = program.checksum_owned(out_name)[1]
+        bounds = comm.allgather((program.slab.begin, program.slab.end))
+        sums = comm.allgather(mine)
+        program.close()
+        if rank == 0:
+            single = CudaProgram(path, device=local_rank)
+            fill_inputs(single)
+            ms1_local, ms1, _ = time_device(single, steps, warmup, None)
+            ref = slab_checksums(single, out_name, bounds)
+            single.close()
+            t1 = ms1 / steps
+            out["one_gpu_ms_per_step"] = t1
+            out["parallel_efficiency"] = t1 / (world * out["ms_per_step"])
+            out["slabs_bit_identical_to_one_gpu"] = bool(all(int(a) == int(b) for a, b in zip(ref, sums)))
+        comm.barrier()
+    else:
+        out["one_gpu_ms_per_step"] = out["ms_per_step"]
+        out["parallel_efficiency"] = 1.0
+        program.close()
+    return out
 
 
 def main():
@@ -245,6 +498,9 @@ def main():
                          "layout J,K,I (1024x80x1024); w1d = config 3 with a 1-D weight w[k] in every stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the configs[4] strong-scaling block (default: measured when --config 1)")
     args = ap.parse_args()
     global VARIANT
     VARIANT = args.variant
@@ -270,23 +526,14 @@ def main():
 
     from stencilflow_b200 import build
     build.build_native()
-    from stencilflow_b200 import programs
-    from stencilflow_b200.cuda_program import CudaProgram
 
     comm = None
     if world > 1:
         from stencilflow_b200 import distributed
-        comm = distributed.TorchComm()
+        comm = distributed.make_comm()
 
-    name, prog, halo = build_config(args.config, scale_i=world if args.scaling == "weak" else 1)
-    path = programs.write_program(prog, name)
-    if world > 1:
-        from stencilflow_b200 import distributed
-        program = distributed.SlabProgram(path, comm, device=local_rank)
-    else:
-        program = CudaProgram(path, device=local_rank)
+    name, prog, path, program = make_program(args.config, world, rank, local_rank, comm, args.scaling)
     peak_gbs, peak_src = load_peaks()
-    fill_inputs(program, index_offsets=getattr(program, "input_index_offsets", lambda: None)())
     rtm = program.rt
 
     cells_total = int(np.prod(prog["dimensions"]))
@@ -294,30 +541,9 @@ def main():
     updates_per_step = nops * cells_total                      # whole job, all ranks
     local_fraction = 1.0 / world
 
-    def barrier():
-        rtm.stream_synchronize()
-        if comm is not None:
-            comm.barrier()
-
-    for _ in range(args.warmup):
-        program.execute()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = program.launch_count
-    e0, e1 = rtm.event_create(), rtm.event_create()
-    barrier()
-    rtm.event_record(e0)
-    for _ in range(args.steps):
-        program.execute()
-    rtm.event_record(e1)
-    rtm.event_synchronize(e1)
-    barrier()
-    ms_local = rtm.elapsed_ms(e0, e1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_local, ms, launches = time_device(program, args.steps, args.warmup, comm, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    ms = comm.max_float(ms_local) if comm is not None else ms_local
-    launches = program.launch_count - launches0
     ms_per_step = ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
 
@@ -340,17 +566,35 @@ def main():
     fields = program.program.fields
     min_volume = sum(f.nbytes for f in fields.values() if f.kind in ("input", "output") and not f.is_scalar)
     min_volume *= (1.0 if world == 1 else local_fraction)
+    l0 = program.lowered.launches[0]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_step / lps, "launches_per_step": lps,
                 "operators_per_launch": [len(l.ops) for l in program.lowered.launches],
                 "min_volume_frac": min_volume / (ms_local / args.steps * 1e-3) / 1e9 / peak_gbs,
-                "kernel": program.lowered.launches[0].kernel, "family": program.lowered.launches[0].family}
+                "kernel": l0.kernel, "family": l0.family,
+                "schedule": ("persistent CTAs, work list" if l0.info.get("persistent") else "one CTA per (tile, chunk)")
+                if l0.family == "streamed" else "grid over cells"}
 
-    # end to end through the plugin call with host buffers (pinned), copies inside the timed region
+    # the result the timed executions left behind is checked before anything overwrites it
+    verify = None
+    if not args.no_verify:
+        if world == 1:
+            verify = verify_single(program, prog, path, args.config, local_rank)
+        else:
+            verify = verify_multi(program, prog, path, comm, local_rank)
+
+    # end to end through the plugin call with host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(program, prog, args, updates_per_step, comm)
+
+    plan_desc = [{"family": l.family, "ops": len(l.ops)} for l in program.lowered.launches]
+    program.close()
+
+    strong = None
+    if args.config == 1 and not args.no_strong and VARIANT is None:
+        strong = strong_block(args, world, rank, local_rank, comm, peak_gbs)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -364,72 +608,116 @@ def main():
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if "float64" in json.dumps(prog["program"]) else "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.config, prog),
-                       "per_gpu": "x".join(map(str, [prog["dimensions"][0] // world] + prog["dimensions"][1:])),
-                       "l2": "no flush needed: every pass streams fields of {:.1f} GiB, far above the 126 MB L2".format(
-                           cells_total / world * (8 if "float64" in json.dumps(prog["program"]) else 4) / 2 ** 30),
-                       "plan": [{"family": l.family, "ops": len(l.ops)} for l in program.lowered.launches],
-                       "input": "U[0,1) counter hash generated in HBM (seed 1234)"},
+            "config": common_config(args.config, prog, world, args.scaling),
+            "plan": plan_desc,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "verify": verify, "strong": strong,
             "gpu_launches": launches,
         }
         print(json.dumps(line), flush=True)
-    program.close()
     if comm is not None:
         comm.close()
 
 
+def pcie_duplex_rate(rtm, nbytes=1 << 30):
+    """Measured ceiling of the end-to-end call: host->device and device->host copies of ``nbytes`` each
+    running concurrently on two streams from pinned memory (GB/s per direction)."""
+    a, pa = rtm.host_alloc((nbytes,), np.uint8)
+    b, pb = rtm.host_alloc((nbytes,), np.uint8)
+    d0, d1 = rtm.malloc(nbytes), rtm.malloc(nbytes)
+    s0, s1 = rtm.stream_create(), rtm.stream_create()
+    best = 0.0
+    for it in range(3):
+        rtm.stream_synchronize(s0)
+        rtm.stream_synchronize(s1)
+        t0 = time.perf_counter()
+        rtm.h2d(d0, a, stream=s0)
+        rtm.d2h(b, d1, stream=s1)
+        rtm.stream_synchronize(s0)
+        rtm.stream_synchronize(s1)
+        dt = time.perf_counter() - t0
+        if it:
+            best = max(best, nbytes / dt / 1e9)
+    rtm.free(d0)
+    rtm.free(d1)
+    rtm.host_free(pa)
+    rtm.host_free(pb)
+    return best
+
+
 def measure_e2e(program, prog, args, updates_per_step, comm=None):
     """Same metric through the reference-facing call with HOST buffers: every step copies this rank's
-    inputs host->device from pinned memory, runs the program and copies its outputs back
-    (``CudaProgram.__call__`` on one GPU; the slab-wise equivalent on several).  Wall-clock, max over ranks."""
+    inputs host->device, runs the program and copies its outputs back (``CudaProgram.__call__`` on one
+    GPU; the slab-wise equivalent on several).  Wall-clock, max over ranks.  The headline figure uses
+    plain numpy arrays, as the reference's driver allocates them (``run_program.py:145-159``; the call
+    page-locks them on first use); ``pinned`` repeats it with ``sfb_host_alloc`` memory."""
     rtm = program.rt
     fields = program.program.fields
-    host_in, host_out, free_host = {}, {}, []
-    h2d = d2h = 0
-    for name, f in fields.items():
-        if f.is_scalar or f.kind == "intermediate":
-            continue
-        shape = program.local_shape(name)
-        if f.kind == "input":
-            arr, hptr = rtm.host_alloc(shape, f.data_type.type)
-            rtm.d2h(arr, program.buffers[name].dptr)         # reuse the synthetic field as host data
-            rtm.stream_synchronize()
-            host_in[name] = arr
-            h2d += arr.nbytes
-        else:
-            arr, hptr = rtm.host_alloc(shape, f.data_type.type)
-            host_out[name] = arr
-            d2h += arr.nbytes
-        free_host.append(hptr)
+
+    def allocate(pinned):
+        host_in, host_out, free_host = {}, {}, []
+        for name, f in fields.items():
+            if f.is_scalar or f.kind == "intermediate":
+                continue
+            shape = program.local_shape(name)
+            if pinned:
+                arr, hptr = rtm.host_alloc(shape, f.data_type.type)
+                free_host.append(hptr)
+            else:
+                arr = np.empty(shape, dtype=f.data_type.type)
+            if f.kind == "input":
+                rtm.d2h(arr, program.buffers[name].dptr)         # reuse the synthetic field as host data
+                rtm.stream_synchronize()
+                host_in[name] = arr
+            else:
+                host_out[name] = arr
+        return host_in, host_out, free_host
+
     steps = max(2, min(args.steps, 5))
 
-    def one_step():
-        # the reference-facing call: CudaProgram.__call__ / SlabProgram.__call__ with host arrays
+    def timed(host_in, host_out):
         kw = {k + "_host": v for k, v in host_in.items()}
         kw.update({k + "_host": v for k, v in host_out.items()})
-        program(**kw)
+        program(**kw)                                            # warm (page-locks numpy arrays once)
+        if comm is not None:
+            comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            # the reference-facing call: CudaProgram.__call__ / SlabProgram.__call__ with host arrays
+            program(**kw)
+        rtm.stream_synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        h2d = sum(a.nbytes for a in host_in.values())
+        d2h = sum(a.nbytes for a in host_out.values())
+        copied = getattr(program, "last_call_bytes", None)
+        if copied:                                               # bytes the call actually moved per step
+            h2d, d2h = int(copied[0]), int(copied[1])
+        if comm is not None:
+            dt = comm.max_float(dt)
+            h2d = int(sum(comm.allgather(h2d)))
+            d2h = int(sum(comm.allgather(d2h)))
+        return dt, h2d, d2h
 
-    one_step()                                               # warm
-    if comm is not None:
-        comm.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
-    rtm.stream_synchronize()
-    dt = (time.perf_counter() - t0) / steps
-    copied = getattr(program, "last_call_bytes", None)
-    if copied:                                               # bytes the call actually moved per step
-        h2d, d2h = int(copied[0]), int(copied[1])
-    if comm is not None:
-        dt = comm.max_float(dt)
-        h2d = int(sum(comm.allgather(h2d)))
-        d2h = int(sum(comm.allgather(d2h)))
+    host_in, host_out, _ = allocate(False)
+    dt, h2d, d2h = timed(host_in, host_out)
+    del host_in, host_out
+    host_in, host_out, free_host = allocate(True)
+    dt_pinned, _, _ = timed(host_in, host_out)
     for hptr in free_host:
         rtm.host_free(hptr)
-    return {"value": updates_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": steps,
-            "host_memory": "pinned (cudaHostAlloc)"}
+    link = pcie_duplex_rate(rtm) if comm is None else None
+    out = {"value": updates_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": steps,
+           "host_memory": "numpy arrays (pageable when handed over; page-locked by the call on first use)",
+           "pinned": {"value": updates_per_step / dt_pinned, "ms_per_step": dt_pinned * 1e3,
+                      "host_memory": "sfb_host_alloc (cudaHostAlloc)"}}
+    if link:
+        # both directions run concurrently, so the call cannot be faster than its larger direction
+        world = 1 if comm is None else comm.world
+        floor = max(h2d, d2h) / world / (link * 1e9)
+        out["roofline"] = {"bound": "pcie", "peak": link, "unit": "GB/s per direction, H2D and D2H concurrently",
+                           "achieved": max(h2d, d2h) / world / dt / 1e9, "frac": floor / dt}
+    return out
 
 
 if __name__ == "__main__":

@@ -109,7 +109,9 @@ SFB_API int sfb_free(void* dptr);
 SFB_API int sfb_memset(void* dptr, int byte_value, size_t bytes, void* stream);
 SFB_API int sfb_host_alloc(void** hptr, size_t bytes);          /* pinned host memory */
 SFB_API int sfb_host_free(void* hptr);
-SFB_API int sfb_host_register(void* hptr, size_t bytes);        /* pin caller-owned memory */
+/* Page-locks caller-owned memory (numpy arrays of the reference driver, stencilflow/run_program.py:145-159).
+ * Returns 1 (not an error) when the range is page-locked already; only a 0 return has to be undone. */
+SFB_API int sfb_host_register(void* hptr, size_t bytes);
 SFB_API int sfb_host_unregister(void* hptr);
 SFB_API int sfb_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
 SFB_API int sfb_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);

@@ -492,7 +492,12 @@ int sfb_host_free(void* hptr) {
 }
 
 int sfb_host_register(void* hptr, size_t bytes) {
-    SFB_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterDefault));
+    cudaError_t e = cudaHostRegister(hptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();       // page-locked already (sfb_host_alloc memory, an earlier registration)
+        return 1;
+    }
+    SFB_CUDA(e);
     return SFB_OK;
 }
 

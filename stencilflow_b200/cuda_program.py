@@ -141,6 +141,7 @@ class CudaProgram:
     def close(self):
         if self.rt is None:
             return
+        self._unpin_all()
         if self._graph is not None:
             self.rt.graph_destroy(self._graph)
             self._graph = None
@@ -427,6 +428,54 @@ class CudaProgram:
         assert all(d == t[1] for d, t in zip(done, target)) and all(v == own1 for v in out_done.values())
         return schedule
 
+    # ------------------------------------------------------------------ caller-owned host arrays
+    REGISTER_MIN_BYTES = 32 << 20
+
+    def _pin(self, arr):
+        """Page-locks a large caller-owned array (``cudaHostRegister`` through ``sfb_host_register``) so
+        that its copies are asynchronous DMA at full PCIe rate instead of staged through the driver's
+        bounce buffer -- what makes the overlapped call work for the plain numpy arrays the reference
+        driver allocates (``stencilflow/run_program.py:145-159``), not only for ``sfb_host_alloc`` memory.
+        Registered once per allocation (cached by address), released when the array dies or the
+        program is closed.  Failure to register is not an error: the copies are merely slower."""
+        import weakref
+        base = arr
+        while isinstance(getattr(base, "base", None), np.ndarray):
+            base = base.base
+        if base.nbytes < self.REGISTER_MIN_BYTES or not base.flags["C_CONTIGUOUS"]:
+            return False
+        pinned = self.__dict__.setdefault("_pinned", {})
+        key = (base.ctypes.data, base.nbytes)
+        if key in pinned:
+            return True
+        try:
+            if not self.rt.host_register(base):
+                pinned[key] = None             # page-locked already (sfb_host_alloc memory, another program)
+                return True
+        except rt.SfbError:
+            pinned[key] = None
+            return False
+        addr, rtm = base.ctypes.data, self.rt
+
+        def release(addr=addr, key=key, pinned=pinned, rtm=rtm):
+            if pinned.pop(key, None) is not None:
+                try:
+                    rtm.lib.sfb_host_unregister(ctypes.c_void_p(addr))
+                except Exception:
+                    pass
+
+        try:
+            pinned[key] = weakref.finalize(base, release)
+        except TypeError:                      # not weak-referenceable: keep it registered until close()
+            pinned[key] = release
+        return True
+
+    def _unpin_all(self):
+        for key, fin in list(self.__dict__.get("_pinned", {}).items()):
+            if fin is not None:
+                fin()
+        self.__dict__["_pinned"] = {}
+
     def _call_pipelined(self, arrays, pieces):
         key = ("pipeline", pieces)
         if getattr(self, "_pipe_key", None) != key or self._packs is None:
@@ -450,6 +499,7 @@ class CudaProgram:
                     or arr.size != int(np.prod(self.local_shape(name)))):
                 return False
             flat[name] = arr.reshape(-1)
+            self._pin(arr)
         base = self.slab.alloc_begin if self.slab is not None else 0     # first plane the buffers hold
         copied = [0, 0]
         start = rtm.event_create(False)

@@ -272,6 +272,102 @@ class TorchComm(Comm):
             self.dist.destroy_process_group()
 
 
+class SocketComm(Comm):
+    """Rendezvous over plain TCP on one box, no dependencies: rank 0 listens on
+    ``MASTER_ADDR:SFB200_COMM_PORT`` (default ``MASTER_PORT + 1``), the other ranks connect; every
+    collective is an all-gather of pickled objects through rank 0.  Carries a few hundred bytes (IPC
+    handles, timings) -- the data path is NVLink."""
+
+    def __init__(self, rank=None, world=None, addr=None, port=None, timeout=120.0):
+        import socket
+        import time
+        self.rank = int(os.environ["RANK"]) if rank is None else rank
+        self.world = int(os.environ["WORLD_SIZE"]) if world is None else world
+        addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(port or os.environ.get("SFB200_COMM_PORT", 0) or int(os.environ.get("MASTER_PORT", "29500")) + 1)
+        self.peers = []
+        self.sock = None
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(self.world)
+            srv.settimeout(timeout)
+            conns = {}
+            while len(conns) < self.world - 1:
+                c, _ = srv.accept()
+                c.settimeout(timeout)
+                c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                r = pickle.loads(self._recv(c))
+                conns[r] = c
+            srv.close()
+            self.peers = [conns[r] for r in range(1, self.world)]
+        else:
+            deadline = time.time() + timeout
+            while True:
+                try:
+                    self.sock = socket.create_connection((addr, port), timeout=timeout)
+                    break
+                except OSError:
+                    if time.time() > deadline:
+                        raise
+                    time.sleep(0.05)
+            self.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            self._send(self.sock, pickle.dumps(self.rank))
+
+    @staticmethod
+    def _send(sock, payload):
+        sock.sendall(len(payload).to_bytes(8, "little") + payload)
+
+    @staticmethod
+    def _recv(sock):
+        def exactly(n):
+            buf = bytearray()
+            while len(buf) < n:
+                chunk = sock.recv(n - len(buf))
+                if not chunk:
+                    raise ConnectionError("peer closed the rendezvous connection")
+                buf += chunk
+            return bytes(buf)
+        return exactly(int.from_bytes(exactly(8), "little"))
+
+    def allgather(self, obj):
+        if self.world == 1:
+            return [obj]
+        if self.rank == 0:
+            out = [obj] + [pickle.loads(self._recv(c)) for c in self.peers]
+            payload = pickle.dumps(out)
+            for c in self.peers:
+                self._send(c, payload)
+            return out
+        self._send(self.sock, pickle.dumps(obj))
+        return pickle.loads(self._recv(self.sock))
+
+    def barrier(self):
+        self.allgather(None)
+
+    def max_float(self, x):
+        return max(self.allgather(float(x)))
+
+    def close(self):
+        for c in self.peers + ([self.sock] if self.sock else []):
+            try:
+                c.close()
+            except OSError:
+                pass
+        self.peers, self.sock = [], None
+
+
+def make_comm():
+    """The rendezvous of this launch: ``SFB200_COMM`` = ``socket`` (plain TCP, what ``bin/run_distributed_program.py``
+    uses for the ranks it starts itself) or ``torch`` (``torch.distributed``/gloo -- the default under
+    ``torchrun``, whose own store already owns ``MASTER_PORT``)."""
+    kind = os.environ.get("SFB200_COMM", "torch" if "TORCHELASTIC_RUN_ID" in os.environ else "socket")
+    return SocketComm() if kind == "socket" else TorchComm()
+
+
 # ------------------------------------------------------------------------------------ device side
 
 

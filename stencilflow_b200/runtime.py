@@ -261,7 +261,13 @@ class Runtime:
         _check(self.lib.sfb_host_free(_vp(hptr)))
 
     def host_register(self, arr):
-        _check(self.lib.sfb_host_register(_vp(arr.ctypes.data), arr.nbytes))
+        """True if this call page-locked the array (and ``host_unregister`` has to undo it), False if
+        it was page-locked already."""
+        status = self.lib.sfb_host_register(_vp(arr.ctypes.data), arr.nbytes)
+        if status == 1:
+            return False
+        _check(status)
+        return True
 
     def host_unregister(self, arr):
         _check(self.lib.sfb_host_unregister(_vp(arr.ctypes.data)))

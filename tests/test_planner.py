@@ -168,7 +168,7 @@ def test_reference_arm_line(monkeypatch):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     env.pop("SFB200_REF_THREADS", None)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "0",
-                          "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, text=True, env=env, timeout=300,
+                          "--steps", "3", "--warmup", "1"], stdout=subprocess.PIPE, text=True, env=env, timeout=300,
                          check=True).stdout
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "stencil_cell_updates_per_s"
@@ -177,6 +177,9 @@ def test_reference_arm_line(monkeypatch):
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert line["ms_per_step"] > 0 and "32x32x32" in line["config"]["workload"]
+    # exactly the requested number of timed executions; the same config keys as the GPU arm prints
+    assert line["steps"] == 3 and line["warmup"] == 1
+    assert set(line["config"]) == {"workload", "per_gpu", "l2", "input"}
 
 
 def test_choose_chunk_balances_waves_and_warmup():
