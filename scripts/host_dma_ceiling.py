@@ -49,6 +49,30 @@ def main():
         rates = comm.allgather(rate)
         results[mode] = {"per_rank_gbs_per_direction": [round(r, 2) for r in rates],
                          "aggregate_gbs_per_direction": round(sum(rates), 2)}
+    # the same with caller-owned numpy memory page-locked by sfb_host_register (what the reference-facing call does)
+    ra, rb = np.empty(nbytes, np.uint8), np.empty(nbytes, np.uint8)
+    ra[:] = 1
+    rtm.host_register(ra)
+    rtm.host_register(rb)
+    for mode in ("h2d", "d2h", "duplex"):
+        for it in range(2):
+            rtm.stream_synchronize(s0)
+            rtm.stream_synchronize(s1)
+            comm.barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                if mode in ("h2d", "duplex"):
+                    rtm.h2d(d0, ra, stream=s0)
+                if mode in ("d2h", "duplex"):
+                    rtm.d2h(rb, d1, stream=s1)
+            rtm.stream_synchronize(s0)
+            rtm.stream_synchronize(s1)
+            dt = time.perf_counter() - t0
+        rates = comm.allgather(4 * nbytes / dt / 1e9)
+        results["registered_" + mode] = {"per_rank_gbs_per_direction": [round(r, 2) for r in rates],
+                                         "aggregate_gbs_per_direction": round(sum(rates), 2)}
+    rtm.host_unregister(ra)
+    rtm.host_unregister(rb)
     if rank == 0:
         print(json.dumps({"n_gpus": world, "bytes_per_copy": nbytes, "host_cores": os.cpu_count(), **results}), flush=True)
     rtm.free(d0)

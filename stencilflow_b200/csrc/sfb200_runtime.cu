@@ -18,6 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <string>
 
 namespace {
@@ -43,6 +46,7 @@ int fail(int code, const char* fmt, ...) {
                         : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)       \
                               ? SFB_ERR_NO_DEVICE                                               \
                               : SFB_ERR_CUDA;                                                   \
+            (void)cudaGetLastError(); /* this call reports its own failure: leave nothing behind */ \
             return fail(code_, "%s failed: %s (%s)", #call, cudaGetErrorString(e_),             \
                         cudaGetErrorName(e_));                                                  \
         }                                                                                       \
@@ -492,6 +496,12 @@ int sfb_host_free(void* hptr) {
 }
 
 int sfb_host_register(void* hptr, size_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    {   // pages not touched yet come as huge pages: fewer, larger DMA descriptors (advice only, errors ignored)
+        uintptr_t lo = ((uintptr_t)hptr + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)hptr + bytes) & ~(uintptr_t)4095;
+        if (hi > lo) (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+    }
+#endif
     cudaError_t e = cudaHostRegister(hptr, bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) {
         (void)cudaGetLastError();       // page-locked already (sfb_host_alloc memory, an earlier registration)
@@ -620,6 +630,7 @@ int sfb_fill_constant(void* dptr, uint64_t n, int dtype, double value, void* str
     if (!dptr) return fail(SFB_ERR_INVALID, "dptr is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = grid_for(n, 256);
+    (void)cudaGetLastError();           // the check below is about this launch only
     switch (dtype) {
         case SFB_F32: k_fill_constant<float><<<g, 256, 0, s>>>((float*)dptr, n, (float)value); break;
         case SFB_F64: k_fill_constant<double><<<g, 256, 0, s>>>((double*)dptr, n, value); break;
@@ -637,6 +648,7 @@ int sfb_fill_hash(void* dptr, uint64_t n, int dtype, uint64_t seed, double lo, d
     if (!dptr) return fail(SFB_ERR_INVALID, "dptr is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = grid_for(n, 256);
+    (void)cudaGetLastError();           // the check below is about this launch only
     switch (dtype) {
         case SFB_F32: k_fill_hash<float><<<g, 256, 0, s>>>((float*)dptr, n, seed, lo, hi, index_offset); break;
         case SFB_F64: k_fill_hash<double><<<g, 256, 0, s>>>((double*)dptr, n, seed, lo, hi, index_offset); break;

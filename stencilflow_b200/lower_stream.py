@@ -1703,9 +1703,15 @@ def partition(program: StencilProgram, options):
             group = ops[start:end]
             # structurally identical chain segments (Jacobi chains) share one estimate
             chain = _chain_like(group)
-            key = tuple((repr([op.offsets3(f) for f in op.accesses]),
-                         repr(sorted(op.boundary_conditions.items(), key=repr)[0][1:] if op.boundary_conditions else ""),
-                         op.data_type.name) for op in group) if chain else None
+            # (what decides streamability and cost: taps, boundary handling, result type -- and the
+            # type and dimensionality of the field the chain starts from)
+            key = None
+            if chain:
+                src = program.fields[next(iter(group[0].accesses))]
+                key = (src.data_type.name, tuple(src.dims)) + tuple(
+                    (repr([op.offsets3(f) for f in op.accesses]),
+                     repr(sorted(op.boundary_conditions.items(), key=repr)[0][1:] if op.boundary_conditions else ""),
+                     op.data_type.name, tuple(sorted(op.scalars))) for op in group)
             if chain and key in cache:
                 cost = cache[key]
             else:

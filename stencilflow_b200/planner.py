@@ -242,8 +242,14 @@ def plan_program(program: StencilProgram, options: Optional[PlanOptions] = None,
                 passes.append({"family": "general", "ops": [op.name]})
         else:
             from . import lower_stream
-            lower_stream.lower_group(lowered, ops, options, specialize)
-            passes.append({"family": "streamed", "ops": [op.name for op in ops]})
+            try:
+                lower_stream.lower_group(lowered, ops, options, specialize)
+                passes.append({"family": "streamed", "ops": [op.name for op in ops]})
+            except lower_stream.NotStreamable:
+                # the partition's estimate was wrong about this group: one-operator kernels always work
+                for op in ops:
+                    lower_cuda.lower_general_op(lowered, op, specialize)
+                    passes.append({"family": "general", "ops": [op.name]})
     plan = Plan(program, lowered, passes, options)
     plan.tuned_from = tuned_from
     return plan

@@ -72,15 +72,88 @@ CASES = [
 # (bounded_queue.py:68 len() of unsized object), and/or (compute_graph_nodes BoolOp not implemented).
 
 
+# Cases the reference's simulator cannot run as they are -- ``shrink`` boundaries (kernel.py:534-540 raises
+# NotImplementedError), 2-D programs, operators with several statements -- are handed to it in an
+# EQUIVALENT form, equivalent by the reference's own definitions, and its output is mapped back:
+#   "shrink_const": ``shrink`` is the constant -100000 (stencil/_common.py:8 JUNK_VAL, stencil/cpu.py:91-95);
+#   "inline":       an operator ``t = e1; op = e2(t)`` is the operator ``op = e2((e1))``: the tasklet runs its
+#                   statements in order and they are pure expressions (stencil/cpu.py:141-179).  (Splitting
+#                   it into two operators instead overflows a delay buffer inside the reference's simulator.)
+#   "embed2d":      a 2-D program over [Nj, Nk] is the 3-D program over [2, Nj, Nk] without i-offsets (the
+#                   reference itself lifts 2-D programs to 3-D, kernel_chain_graph.py:399-403); plane 0 is the result.
+# The stored arrays have the ORIGINAL program's shape; tests run the original program and compare the
+# interior (``halo`` cells from every border excluded, as ``run_program -halo`` does for shrink programs).
+# (case, program, seed, transforms, halo, {input: (lo, hi)})
+TRANSFORMED_CASES = [
+    ("jacobi3d_shrink_via_const", "jacobi3d_24x20x40_4itr_shrink_f64", 21, ["shrink_const"], 4, {}),
+    ("hdiff_shrink_via_const_inline", "hdiff_24x28x16", 22, ["shrink_const", "inline"], 2,
+     {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)}),
+    ("hdiff_f64_shrink_via_const_inline", "hdiff_16x20x8_f64", 23, ["shrink_const", "inline"], 2,
+     {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)}),
+    ("multistmt3d_via_inline", "multistmt3d_6x8x10_f64", 24, ["inline"], 0, {}),
+    ("jacobi2d_shrink_via_const_embed", "jacobi2d_96x128_6itr_shrink_f64", 25, ["shrink_const", "embed2d"], 6, {}),
+    ("ref_jacobi2d_128x128_via_embed", "ref_jacobi2d_128x128", 26, ["embed2d"], 0, {}),
+    ("jacobi2d_const_f32_via_embed", "jacobi2d_64x64_4itr_const_f32", 27, ["embed2d"], 0, {}),
+]
+
+
+def transform_program(prog, inputs, transforms):
+    """(program', inputs', map_back) for the equivalent forms above.  Uses the real ``ast.parse``."""
+    parse = getattr(ast, "_sf_real_parse", ast.parse)
+    prog = json.loads(json.dumps(prog))
+    inputs = dict(inputs)
+    map_back = lambda arr: arr                                          # noqa: E731
+    if "shrink_const" in transforms:
+        for op in prog["program"].values():
+            for bc in op["boundary_conditions"].values():
+                if bc["type"] == "shrink":
+                    bc["type"], bc["value"] = "constant", -100000.0
+    if "inline" in transforms:
+        for name, op in prog["program"].items():
+            stmts = [st.strip() for st in op["computation_string"].split(";") if st.strip()]
+            values = {}
+            for stmt in stmts:
+                tree = parse(stmt)
+                target = tree.body[0].targets[0].id
+
+                class Sub(ast.NodeTransformer):
+                    def visit_Name(self, node):
+                        return parse("(" + values[node.id] + ")", mode="eval").body if node.id in values else node
+
+                values[target] = ast.unparse(Sub().visit(tree.body[0].value))
+            op["computation_string"] = "{} = {}".format(name, values[name])
+    if "embed2d" in transforms:
+        assert len(prog["dimensions"]) == 2
+        prog["dimensions"] = [2] + list(prog["dimensions"])
+
+        class Lift(ast.NodeTransformer):
+            def visit_Subscript(self, node):
+                elts = node.slice.elts if isinstance(node.slice, ast.Tuple) else [node.slice]
+                node.slice = ast.Tuple(elts=[ast.Name(id="i", ctx=ast.Load())] + list(elts), ctx=ast.Load())
+                return node
+
+        for op in prog["program"].values():
+            stmts = []
+            for stmt in op["computation_string"].split(";"):
+                if stmt.strip():
+                    stmts.append(ast.unparse(Lift().visit(parse(stmt.strip()))))
+            op["computation_string"] = "; ".join(stmts)
+        for cfg in prog["inputs"].values():
+            assert "input_dims" not in cfg
+        inputs = {k: np.stack([v, v]) for k, v in inputs.items()}
+        map_back = lambda arr: np.asarray(arr).reshape(prog["dimensions"])[0]     # noqa: E731
+    return prog, inputs, map_back
+
+
 def case_program(program):
     """The program description of a case (a dict, as parsed from tests/programs/<program>.json)."""
     with open(os.path.join(ROOT, "tests", "programs", program + ".json")) as f:
         return json.load(f)
 
 
-def case_inputs(prog, seed):
-    """Inputs of a case as {name: ndarray of the program's shape}: U[0.5, 1.5) from ``seed``, or
-    (seed None) what the program file names -- ``constant:v`` or a list; .dat files are zeros here."""
+def case_inputs(prog, seed, ranges=None):
+    """Inputs of a case as {name: ndarray of the program's shape}: U[0.5, 1.5) (or ``ranges[name]``) from
+    ``seed``, or (seed None) what the program file names -- ``constant:v`` or a list; .dat files are zeros here."""
     shape = tuple(prog["dimensions"])
     out = {}
     rng = np.random.default_rng(seed) if seed is not None else None
@@ -88,7 +161,8 @@ def case_inputs(prog, seed):
         spec = prog["inputs"][name]
         dt = np.dtype(spec["data_type"]).type
         if rng is not None:
-            out[name] = rng.uniform(0.5, 1.5, size=shape).astype(dt)
+            lo, hi = (ranges or {}).get(name, (0.5, 1.5))
+            out[name] = rng.uniform(lo, hi, size=shape).astype(dt)
         elif isinstance(spec["data"], list):
             out[name] = np.array(spec["data"], dtype=dt).reshape(shape)
         elif str(spec["data"]).startswith("constant:"):
@@ -141,6 +215,7 @@ def install_shims():
         _fields = ("value",)
 
     real_parse = ast.parse
+    ast._sf_real_parse = real_parse
 
     def parse(source, *args, **kwargs):
         tree = real_parse(source, *args, **kwargs)
@@ -230,6 +305,26 @@ def main():
                 arrays[case + "/" + field] = np.asarray(arr, dtype=dt).reshape(prog["dimensions"])
             print("{:<40} {:>8} cycles  {}".format(case, cycles, {
                 k: float(np.sum(np.asarray(v, dtype=np.float64))) for k, v in res.items()}), flush=True)
+        for case, program, seed, transforms, halo, ranges in TRANSFORMED_CASES:
+            if only and case not in only:
+                continue
+            prog = case_program(program)
+            inputs = case_inputs(prog, seed, ranges)
+            tprog, tinputs, map_back = transform_program(prog, inputs, transforms)
+            try:
+                res, cycles = run(tprog, tinputs, work, case)
+            except Exception as exc:  # noqa: BLE001
+                lines = [l for l in str(exc).splitlines() if "Error" in l or "Exception" in l]
+                print("{:<40} NOT SIMULATED by the reference: {}".format(case, (lines or [str(exc)[:200]])[-1]), flush=True)
+                continue
+            outputs = sorted(o for o in res if o in prog["outputs"])
+            index[case] = {"program": program, "seed": seed, "cycles": cycles, "outputs": outputs,
+                           "transforms": transforms, "halo": halo, "ranges": ranges}
+            for field in outputs:
+                dt = np.dtype(prog["program"][field]["data_type"])
+                arrays[case + "/" + field] = np.asarray(map_back(np.asarray(res[field])), dtype=dt).reshape(prog["dimensions"])
+            print("{:<40} {:>8} cycles  {}".format(case, cycles, {
+                k: float(np.sum(np.asarray(arrays[case + "/" + k], dtype=np.float64))) for k in outputs}), flush=True)
     np.savez_compressed(OUT_NPZ, **arrays)
     with open(OUT_JSON, "w") as f:
         json.dump(index, f, indent=1, sort_keys=True)

@@ -223,3 +223,35 @@ def test_halo_schedule_of_a_two_pass_chain(native_lib):
     assert sorted((s.launch, s.field, s.peer, s.src_end - s.src_begin) for s in sends) == \
         [(0, "b3", 0, 4), (0, "b3", 2, 4)]
     assert distributed.halo_schedule(p.lowered, distributed.Slab(0, 1, 32, 4)) == []
+
+
+def test_partition_cache_distinguishes_source_type(native_lib, tmp_path):
+    """Two chains with identical taps but sources of different type: float32 operators on a float32
+    field stream, the same operators on a float64 field cannot (mixed types) -- the cost cache of the
+    partition must not carry the first answer over to the second (either order)."""
+    import json
+    from stencilflow_b200.cuda_program import CudaProgram
+
+    def chain(src, names):
+        out, prev = {}, src
+        for n in names:
+            out[n] = {"data_type": "float32", "boundary_conditions": {prev: {"type": "constant", "value": 0.0}},
+                      "computation_string": "{n} = 0.25 * ({p}[i,j,k-1] + {p}[i,j,k+1] + {p}[i-1,j,k] + {p}[i,j+1,k])".format(n=n, p=prev)}
+            prev = n
+        return out
+
+    for order in ((("a", "float32"), ("b", "float64")), (("b", "float64"), ("a", "float32"))):
+        prog = {"dimensions": [16, 16, 32], "outputs": [], "inputs": {}, "program": {}}
+        for k, (src, dt) in enumerate(order):
+            prog["inputs"][src] = {"data": "constant:1.0", "data_type": dt}
+            names = ["o{}_{}".format(k, s) for s in range(2)]
+            prog["program"].update(chain(src, names))
+            prog["outputs"].append(names[-1])
+        path = tmp_path / "mixed_{}.json".format(order[0][0])
+        path.write_text(json.dumps(prog))
+        p = CudaProgram(str(path), allocate=False)
+        fam = {tuple(l.ops): l.family for l in p.lowered.launches}
+        f32 = [ops for ops in fam if ops[0].startswith("o{}_".format([s for s, _ in order].index("a")))]
+        f64 = [ops for ops in fam if ops[0].startswith("o{}_".format([s for s, _ in order].index("b")))]
+        assert all(fam[o] == "streamed" for o in f32), fam
+        assert all(fam[o] == "general" for o in f64), fam
