@@ -497,9 +497,16 @@ int sfb_host_free(void* hptr) {
 
 int sfb_host_register(void* hptr, size_t bytes) {
 #if defined(__linux__) && defined(MADV_HUGEPAGE)
-    {   // pages not touched yet come as huge pages: fewer, larger DMA descriptors (advice only, errors ignored)
+    {   // huge pages: fewer, larger DMA descriptors -- registered 4 KiB pages were measured 12 % (copies in both
+        // directions at once) to 25 % (the overlapped host call) slower than cudaHostAlloc memory; advice only
         uintptr_t lo = ((uintptr_t)hptr + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)hptr + bytes) & ~(uintptr_t)4095;
-        if (hi > lo) (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+        if (hi > lo) {
+            (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+#ifndef MADV_COLLAPSE
+#define MADV_COLLAPSE 25                /* Linux >= 6.1: collapse what is already resident, synchronously */
+#endif
+            if (!getenv("SFB200_NO_COLLAPSE")) (void)madvise((void*)lo, hi - lo, MADV_COLLAPSE);
+        }
     }
 #endif
     cudaError_t e = cudaHostRegister(hptr, bytes, cudaHostRegisterDefault);

@@ -41,6 +41,7 @@ HALO = {
     "jacobi3d_24x20x40_4itr_shrink_f64": 4,
     "lowdim3d_20x24x48_3st_shrink_f64": 4,
     "jacobi2d_96x128_6itr_w1d_shrink_f64": 6,
+    "sdfgexport_hdiff_jki_48x8x64_f64": 2,
 }
 
 # value ranges of the random test inputs; hdiff subtracts a small correction from `inp`, so its
@@ -49,6 +50,7 @@ INPUT_RANGES = {
     "hdiff_24x28x16": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
     "hdiff_16x20x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
     "hdiff_const_10x12x8_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05)},
+    "sdfgexport_hdiff_jki_48x8x64_f64": {"inp": (1.0, 2.0), "coeff": (0.0, 0.05), "wgt": (0.9, 1.1)},
     # hotspot: coefficients of a stable explicit step (the generator's default 0.5 is not)
     "synth_hotspot2d_48x64_4st_f64": {"sdc": (0.05, 0.1), "r_x": (0.5, 1.0), "r_y": (0.5, 1.0), "r_z": (0.5, 1.0),
                                       "amb": (0.5, 1.0)},

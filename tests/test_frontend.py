@@ -197,3 +197,30 @@ class TestKernelChainGraph:
         p.write_text(json.dumps(prog))
         with pytest.raises(ValueError, match="not divisible"):
             make_program(sf.KernelChainGraph(str(p)))
+
+
+def test_exported_program_conventions_parse():
+    """JSON as ``sdfg_to_stencilflow`` emits it (reference sdfg_to_stencilflow.py:522-767): versioned names,
+    ``constants`` with string values and a data type, ``btype`` keys, astunparse's newline-separated
+    statements, ``input_dims`` on every input, the J,K,I layout (vertical axis in the middle)."""
+    from stencilflow_b200.kernel_chain_graph import KernelChainGraph
+    from stencilflow_b200.stencil_op import make_program
+    chain = KernelChainGraph(program_path("sdfgexport_hdiff_jki_48x8x64_f64"))
+    assert chain.dimensions == [48, 8, 64]
+    assert set(chain.kernel_nodes) == {"lap", "flx", "fly", "out__1", "out"}
+    assert chain.constants["dcoef"]["value"] == "0.25"
+    prog = make_program(chain)
+    ops = {op.name: op for op in prog.ops}
+    # the versioned intermediate feeds the final write of the same field
+    assert "out__1" in ops["out"].accesses and prog.fields["out"].kind == "output"
+    assert prog.fields["out__1"].kind == "intermediate"
+    # two statements, the second using the first's temporary
+    assert [s.target for s in ops["flx"].statements] == ["d", "flx"]
+    # boundary keys given as btype
+    assert ops["lap"].boundary_conditions["inp"]["btype"] == "shrink"
+    # the 1-D input lives on the vertical (middle) axis only; the constant is not a field
+    assert list(prog.fields["wgt"].dims) == ["j"] and prog.fields["wgt"].shape == (8,)
+    assert "dcoef" in ops["out"].scalars and "dcoef" not in prog.fields
+    # horizontal offsets sit on the first and the last iterator (J and I of the COSMO layout)
+    taps = ops["lap"].offsets3("inp")
+    assert sorted(tuple(t) for t in taps) == sorted([(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1)])

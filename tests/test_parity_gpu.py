@@ -495,3 +495,29 @@ def test_persistent_schedule_bit_identical_at_scale(gpu, kind, monkeypatch):
             assert l.info["persistent"] and 0.9 * p._resident_ctas(l) <= grid[0] <= p._resident_ctas(l) and grid[1:] == (1, 1)
         p.close()
     assert sums[1][1] == sums[0][1] and sums[2][1] == sums[0][1], sums
+
+
+
+def test_exported_program_conventions_end_to_end(gpu, tmp_path, monkeypatch):
+    """A program as ``sdfg_to_stencilflow`` writes it (``stencilflow/sdfg_to_stencilflow.py:522-767``): J,K,I
+    layout (``:46-68``), versioned field names (``out__1`` -> ``out``), ``constants`` with string values,
+    ``btype`` boundary keys, newline-separated statements from astunparse, raw ``.dat`` inputs named
+    ``<field>_<dims>_<dtype>.dat`` with ``input_dims`` -- through the drop-in driver with -compare-to-reference."""
+    import json
+    from stencilflow_b200 import helper
+    from stencilflow_b200.run_program import run_program
+    name = "sdfgexport_hdiff_jki_48x8x64_f64"
+    with open(program_path(name)) as f:
+        prog = json.load(f)
+    inputs = random_inputs(name, seed=31)
+    for field, cfg in prog["inputs"].items():
+        helper.save_array(inputs[field], str(tmp_path / cfg["data"]))
+    monkeypatch.chdir(tmp_path)
+    assert run_program(program_path(name), "cuda", compare_to_reference=True, halo=2, log_level=0,
+                       input_directory=str(tmp_path)) == 0
+    # and directly against the oracle on the same arrays
+    from oracle import reference_numpy as rn
+    expected = rn.run_reference(program_path(name), inputs)
+    got, prog_obj = _run_cuda(name, inputs)
+    _check(name, got, expected)
+    assert [l.family for l in prog_obj.lowered.launches] == ["streamed"]          # one fused pass
