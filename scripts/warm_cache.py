@@ -23,6 +23,7 @@ def main():
     for name in all_programs():
         jobs.append((program_path(name), PlanOptions(fuse=False)))
         jobs.append((program_path(name), None))
+        jobs.append((program_path(name), PlanOptions(max_depth=8)))
     names3 = ["ref_jacobi3d_32x32x32_8itr_8vec", "jacobi3d_16x24x32_5itr_const1", "jacobi3d_24x20x40_4itr_shrink_f64",
               "hdiff_24x28x16", "fork_join_20x16x24", "box3d_10x12x16"]
     for name, v in itertools.product(names3, T.PLAN_VARIANTS):

@@ -93,6 +93,7 @@ class CudaProgram:
         self._tables = []          # work tables of persistent launches (device memory)
         self._packs = None
         self._graph = None
+        self._capturing = False
         self.scalar_values = {}
         self.launch_count = 0
         if allocate:
@@ -241,21 +242,32 @@ class CudaProgram:
             cache[l.kernel] = per_sm * int(self.rt.props.sm_count)
         return cache[l.kernel]
 
+    GRAPH_MAX_CELLS = 1 << 21
+
     def execute(self, stream=None):
-        """Enqueue every launch of the plan (asynchronous)."""
+        """Enqueue every launch of the plan (asynchronous).  Launch-bound programs -- several launches
+        over a grid so small that each kernel runs for a few microseconds -- go through a captured CUDA
+        graph, which takes the per-launch driver work off the critical path (``SFB200_GRAPH=0``: never)."""
         if self._packs is None:
             self._build_packs()
+        if (stream is None and not self._capturing and self.slab is None and len(self._packs) >= 3
+                and self.program.cells <= self.GRAPH_MAX_CELLS and os.environ.get("SFB200_GRAPH", "1") != "0"):
+            return self.execute_graph()
         for l, fn, grid, pack in self._packs:
             self.rt.launch(fn, grid, l.block, l.smem, pack.array, stream)
         self.launch_count += len(self._packs)
 
     def execute_graph(self):
         """Same as :meth:`execute` through a captured CUDA graph (launch-bound programs)."""
+        if self._packs is None:
+            self._build_packs()
         if self._graph is None:
             self.rt.graph_begin()
+            self._capturing = True
             try:
                 self.execute()
             finally:
+                self._capturing = False
                 self._graph = self.rt.graph_end()
         else:
             self.launch_count += len(self._packs)

@@ -83,17 +83,69 @@ __device__ __forceinline__ bool sf_elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// L2 eviction priorities (the encodings CUTLASS passes as TMA cache hints): SF_LOAD_HINT / SF_STORE_HINT are
+// defined by the generator when a plan asks for them (input planes are re-read by the neighbouring tiles:
+// keep them; results are written once: let them go first)
+#define SF_L2_EVICT_FIRST 0x12F0000000000000ull
+#define SF_L2_EVICT_LAST 0x14F0000000000000ull
 __device__ __forceinline__ void sf_tma_load_3d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2) {
+#ifdef SF_LOAD_HINT
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(SF_LOAD_HINT)
+        : "memory");
+#else
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void sf_tma_load_2d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1) {
+#ifdef SF_LOAD_HINT
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1), "l"(SF_LOAD_HINT)
+        : "memory");
+#else
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(sf_smem_addr(dst)), "l"(map), "r"(sf_smem_addr(bar)), "r"(c0), "r"(c1)
         : "memory");
+#endif
+}
+#ifdef SF_STORE_HINT
+#define SF_STG_V4F32 "st.global.L2::cache_hint.v4.f32 [%1], {%2, %3, %4, %5}, %6;"
+#define SF_STG_V2F64 "st.global.L2::cache_hint.v2.f64 [%1], {%2, %3}, %4;"
+#define SF_STG_HINT_ARG , "l"(SF_STORE_HINT)
+#else
+#define SF_STG_V4F32 "st.global.v4.f32 [%1], {%2, %3, %4, %5};"
+#define SF_STG_V2F64 "st.global.v2.f64 [%1], {%2, %3};"
+#define SF_STG_HINT_ARG
+#endif
+// ---- slab mode: edge planes of a result go to the neighbouring GPU's halo planes (peer stores over NVLink) ----
+// Run by all threads of a CTA after it has streamed a segment: planes [p0, p1), rows [j0, j1), columns
+// [k0, k1) of its own result -- just written, L2-resident -- are copied to the same cells of the
+// neighbour's buffer, `delta` bytes away in the unified address space.  Doing this once per segment
+// instead of next to the result stores keeps the streamed loop free of extra live registers.
+__device__ __forceinline__ float4 sf_ldcg16(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ double2 sf_ldcg16(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void sf_st16(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void sf_st16(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+template <typename T>
+__device__ __forceinline__ void sf_push_planes(T* own, i64 delta, int p0, int p1, int s_base,
+                                               int j0, int j1, int k0, int k1, int NJ, int NK) {
+    constexpr int W = 16 / (int)sizeof(T);
+    const int kv = (k1 - k0) / W, rows = j1 - j0;
+    if (p1 <= p0 || kv <= 0 || rows <= 0) return;
+    const i64 per_plane = (i64)rows * kv;
+    const i64 total = per_plane * (p1 - p0);
+    for (i64 e = threadIdx.x; e < total; e += blockDim.x) {
+        const int p = p0 + (int)(e / per_plane);
+        const int r = (int)(e % per_plane);
+        T* src = own + (((i64)(p - s_base) * NJ + (j0 + r / kv)) * NK + (k0 + (r % kv) * W));
+        sf_st16(reinterpret_cast<T*>(reinterpret_cast<char*>(src) + delta), sf_ldcg16(src));
+    }
 }
 // ---- neighbour-only synchronisation ("pair" mode) ----
 // Warp w exchanges data with warps w-1 and w+1 only, so instead of one CTA-wide barrier per streamed
@@ -147,24 +199,24 @@ __device__ __forceinline__ void sf_stg_if(bool on, float* p, const float2 (&s)[N
 #pragma unroll
     for (int q = 0; q < N; q += 2)
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
-                     "@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
-                     ::"r"((u32)on), "l"(p + 2 * q), "f"(s[q].x), "f"(s[q].y), "f"(s[q + 1].x), "f"(s[q + 1].y) : "memory");
+                     "@q " SF_STG_V4F32 "\n\t}"
+                     ::"r"((u32)on), "l"(p + 2 * q), "f"(s[q].x), "f"(s[q].y), "f"(s[q + 1].x), "f"(s[q + 1].y) SF_STG_HINT_ARG : "memory");
 }
 template <int N>
 __device__ __forceinline__ void sf_stg_if(bool on, float* p, const float (&s)[N]) {
 #pragma unroll
     for (int q = 0; q < N; q += 4)
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
-                     "@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
-                     ::"r"((u32)on), "l"(p + q), "f"(s[q]), "f"(s[q + 1]), "f"(s[q + 2]), "f"(s[q + 3]) : "memory");
+                     "@q " SF_STG_V4F32 "\n\t}"
+                     ::"r"((u32)on), "l"(p + q), "f"(s[q]), "f"(s[q + 1]), "f"(s[q + 2]), "f"(s[q + 3]) SF_STG_HINT_ARG : "memory");
 }
 template <int N>
 __device__ __forceinline__ void sf_stg_if(bool on, double* p, const double (&s)[N]) {
 #pragma unroll
     for (int q = 0; q < N; q += 2)
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
-                     "@q st.global.v2.f64 [%1], {%2, %3};\n\t}"
-                     ::"r"((u32)on), "l"(p + q), "d"(s[q]), "d"(s[q + 1]) : "memory");
+                     "@q " SF_STG_V2F64 "\n\t}"
+                     ::"r"((u32)on), "l"(p + q), "d"(s[q]), "d"(s[q + 1]) SF_STG_HINT_ARG : "memory");
 }
 __device__ __forceinline__ void sf_sts_if(bool on, float* p, float v) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.f32 [%1], %2;\n\t}"
@@ -188,6 +240,21 @@ __device__ __forceinline__ void sf_stp(float* __restrict__ p, const float2* src)
     *reinterpret_cast<SfVec<float, V>*>(p) = t;
 }
 """
+
+
+def l2_hint_defines():
+    """``SFB200_L2HINT``: bit 0 = input planes are loaded with L2 evict-last priority, bit 1 = results are
+    stored with evict-first priority (default: neither; measured)."""
+    bits = int(os.environ.get("SFB200_L2HINT", L2_HINT_DEFAULT))
+    text = ""
+    if bits & 1:
+        text += "#define SF_LOAD_HINT 0x14F0000000000000ull\n"
+    if bits & 2:
+        text += "#define SF_STORE_HINT 0x12F0000000000000ull\n"
+    return text
+
+
+L2_HINT_DEFAULT = "0"
 
 
 class NotStreamable(Exception):
@@ -886,6 +953,20 @@ class StreamKernelGen:
         if static_d and (U // g.D) % 2 == 1:
             e("phase ^= 1u;", 2)
         e("}")
+        if self.peer_push:
+            # slab mode: the planes of this segment that a neighbouring GPU reads as halo follow the
+            # segment out (all result stores of the CTA are visible to it after the barrier)
+            j0 = "tile_j0" if ndim == 3 else "0"
+            j1 = "min(tile_j0 + {}, {})".format(g.BJ, self.NJ) if ndim == 3 else "1"
+            for n in range(len(stored)):
+                e("if (c_begin < pe_lo_{n} || c_end > pb_hi_{n}) {{".format(n=n))
+                e("__syncthreads();", 2)
+                for (d, lo, hi) in (("pd_lo", "c_begin", "min(c_end, pe_lo_{})".format(n)),
+                                    ("pd_hi", "max(c_begin, pb_hi_{})".format(n), "c_end")):
+                    e("sf_push_planes<{T}>(o_{n}, {d}_{n}, {lo}, {hi}, s_base, {j0}, {j1}, tile_k0, min(tile_k0 + {BK}, {NK}), {NJ}, {NK});".format(
+                        T=T, n=n, d=d, lo=lo, hi=hi, j0=j0, j1=j1, BK=g.BK, NK=self.NK,
+                        NJ=self.NJ if ndim == 3 else 1), 2)
+                e("}")
         if self.persistent:
             e("__syncthreads();")
             e("if (threadIdx.x == 0) *sf_item = (int)gridDim.x + atomicAdd(&work_tab[0], 1);")
@@ -1264,18 +1345,6 @@ class StreamKernelGen:
             for r in range(R):
                 e("sf_stg_if(inchunk && ({sm} & {m}u), op + {o}, nv[{r}]);".format(
                     sm="smask", m=1 << r, o=r * self.NK, r=r), 3)
-            if self.peer_push:
-                # the few planes next to a slab boundary also go to the neighbour that reads them as halo
-                e("if (inchunk && (({p}) < pe_lo_{n} || ({p}) >= pb_hi_{n})) {{".format(p=plane, n=idx), 3)
-                for side, cond in (("lo", "({p}) < pe_lo_{n}"), ("hi", "({p}) >= pb_hi_{n}")):
-                    e("if ({}) {{".format(cond.format(p=plane, n=idx)), 4)
-                    e("{T}* pp = reinterpret_cast<{T}*>(reinterpret_cast<char*>(op) + pd_{s}_{n});".format(
-                        T=T, s=side, n=idx), 5)
-                    for r in range(R):
-                        e("sf_stg_if(({sm} & {m}u) != 0u, pp + {o}, nv[{r}]);".format(
-                            sm="smask", m=1 << r, o=r * self.NK, r=r), 5)
-                    e("}", 4)
-                e("}", 3)
         self._finish_field(info, plane, u)
         e("}", 2)
 
@@ -1591,6 +1660,10 @@ ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0, 5: 1.0}
 # hide each other's barrier and exchange latency
 SMALL_CTA_FACTOR_2D = {1: 1.03, 2: 1.14, 4: 1.06}
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
+LAUNCH_LATENCY = 2.4e-6                     # a small kernel behind another on one stream (8 launches of 32^3: 19.4 us)
+# one streamed plane step per fused operator when nothing else limits it: barrier + exchange of a CTA, which
+# grows with its warps (12-warp 3-D CTAs: 9 steps of 4 operators on 32^3 in 12 us; 2-warp 2-D CTAs: 0.05 us)
+STEP_LATENCY_PER_WARP = 0.018e-6
 
 
 def _tile_efficiency(ana, geo):
@@ -1615,7 +1688,15 @@ def modelled_time(program, ops, ana, geo):
     rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), table[ana.dtype.bytes]))
     rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else SMALL_CTA_FACTOR_2D.get(geo.NT // 32, 1.0)
     t_cmp = program.cells * len(ops) / (eff * used) / rate
-    return max(t_mem, t_cmp) + 5e-6
+    # latency floor: a CTA streams its planes one after the other, warm-up planes included, however few
+    # cells a plane has (what a 32^3 grid costs: 9 steps of 4 fused operators measured 12 us)
+    tiles = -(-nk // geo.BK) * (-(-program.shape[-2] // geo.BJ) if ana.ndim == 3 else 1)
+    slots = SM_COUNT * resident_estimate(geo)
+    overhead = ana.t_end_offset() - ana.t_begin_offset()
+    n_stream = program.shape[0]
+    steps = overhead + (-(-n_stream * tiles // slots) if tiles >= slots else -(-n_stream // (slots // tiles)))
+    t_lat = steps * STEP_LATENCY_PER_WARP * (geo.NT // 32) * len(ops)
+    return max(t_mem, t_cmp, t_lat) + LAUNCH_LATENCY
 
 
 def choose_geometry(program, ops, options):
@@ -1672,7 +1753,7 @@ def group_cost(program, ops, options):
 def general_cost(program, op):
     fields = program.fields
     nbytes = fields[op.name].nbytes + sum(fields[f].nbytes for f in op.accesses)
-    return nbytes / (HBM_BYTES_PER_S * GENERAL_EFFICIENCY) + 5e-6
+    return nbytes / (HBM_BYTES_PER_S * GENERAL_EFFICIENCY) + LAUNCH_LATENCY
 
 
 def partition(program: StencilProgram, options):
@@ -1719,10 +1800,13 @@ def partition(program: StencilProgram, options):
                 if chain:
                     cache[key] = cost
             family = "streamed"
-            if cost is None:
-                if len(group) > 1:
-                    continue
-                cost, family = general_cost(program, group[0]), "general"
+            if len(group) == 1:
+                # a single operator may also be cheaper as a one-operator kernel (tiny grids: no warm-up planes)
+                alone = general_cost(program, group[0])
+                if cost is None or alone < cost:
+                    cost, family = alone, "general"
+            elif cost is None:
+                continue
             if best[start] is None:
                 continue
             total = best[start] + cost

@@ -31,7 +31,8 @@ def main():
     else:
         path = conftest.program_path(name)
         inputs = conftest.random_inputs(name, seed=21)
-    opts = PlanOptions(fuse=fuse)
+    # fusion requested explicitly: the cost model prefers one-operator kernels on grids this small
+    opts = PlanOptions(fuse=fuse, max_depth=(int(os.environ.get("SFB200_MAX_DEPTH", "4")) if fuse else None))
     prog = distributed.SlabProgram(path, comm, device=local_rank, plan_options=opts)
     scalars = {k: v for k, v in inputs.items() if getattr(v, "ndim", 0) == 0}
     if scalars:

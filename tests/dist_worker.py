@@ -42,7 +42,8 @@ def main():
     comm = distributed.TorchComm("gloo")
     prog = rn.load_program(path)
     info = rn.ProgramInfo(prog)
-    plan = CudaProgram(path, allocate=False, plan_options=PlanOptions(fuse=fuse))
+    # fusion requested explicitly: the cost model prefers one-operator kernels on grids this small
+    plan = CudaProgram(path, allocate=False, plan_options=PlanOptions(fuse=fuse, max_depth=4 if fuse else None))
     lowered = plan.lowered
     axis = lowered.slab_axis
     n = plan.program.shape3[axis]

@@ -65,6 +65,18 @@ def test_program_matches_oracle_planned(gpu, name):
     _check(name, got, expected)
 
 
+@pytest.mark.parametrize("name", all_programs())
+def test_program_matches_oracle_fused(gpu, name):
+    """Every program with fusion requested (``max_depth=8``: the longest streamable runs of up to eight
+    operators, whatever the cost model would say about grids this small)."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    inputs = random_inputs(name, seed=17)
+    expected = rn.run_reference(program_path(name), inputs)
+    got, _ = _run_cuda(name, inputs, PlanOptions(max_depth=8))
+    _check(name, got, expected)
+
+
 @pytest.mark.parametrize("name", [n for n in all_programs() if n.startswith("ref_")])
 def test_reference_programs_match_known_answers(gpu, name):
     """The reference's own programs with their own inputs against the frozen known answers."""

@@ -241,17 +241,18 @@ def test_partition_cache_distinguishes_source_type(native_lib, tmp_path):
         return out
 
     for order in ((("a", "float32"), ("b", "float64")), (("b", "float64"), ("a", "float32"))):
-        prog = {"dimensions": [16, 16, 32], "outputs": [], "inputs": {}, "program": {}}
+        prog = {"dimensions": [96, 128, 256], "outputs": [], "inputs": {}, "program": {}}
         for k, (src, dt) in enumerate(order):
             prog["inputs"][src] = {"data": "constant:1.0", "data_type": dt}
-            names = ["o{}_{}".format(k, s) for s in range(2)]
+            names = ["o{}_{}".format(src, s) for s in range(3)]
             prog["program"].update(chain(src, names))
             prog["outputs"].append(names[-1])
         path = tmp_path / "mixed_{}.json".format(order[0][0])
         path.write_text(json.dumps(prog))
-        p = CudaProgram(str(path), allocate=False)
-        fam = {tuple(l.ops): l.family for l in p.lowered.launches}
-        f32 = [ops for ops in fam if ops[0].startswith("o{}_".format([s for s, _ in order].index("a")))]
-        f64 = [ops for ops in fam if ops[0].startswith("o{}_".format([s for s, _ in order].index("b")))]
-        assert all(fam[o] == "streamed" for o in f32), fam
-        assert all(fam[o] == "general" for o in f64), fam
+        p = CudaProgram(str(path), allocate=False)            # must plan without raising in either order
+        fam = {op: l.family for l in p.lowered.launches for op in l.ops}
+        group = {op: tuple(l.ops) for l in p.lowered.launches for op in l.ops}
+        # the float32 chain on the float32 field streams ...
+        assert all(fam["oa_{}".format(k)] == "streamed" for k in range(3)), (fam, group)
+        # ... the operator reading the float64 field into a float32 result cannot (mixed types)
+        assert fam["ob_0"] == "general", (fam, group)
