@@ -328,6 +328,7 @@ def time_device(program, steps, warmup, comm, sampler=None):
     rtm.event_destroy(e0)
     rtm.event_destroy(e1)
     ms = comm.max_float(ms_local) if comm is not None else ms_local
+    time_device.per_rank_ms = comm.allgather(ms_local) if comm is not None else [ms_local]
     return ms_local, ms, program.launch_count - launches0
 
 
@@ -544,6 +545,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_local, ms, launches = time_device(program, args.steps, args.warmup, comm, sampler)
     clocks = sampler.stop() if rank == 0 else None
+    per_rank_ms = [t / args.steps for t in time_device.per_rank_ms]
     ms_per_step = ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
 
@@ -604,7 +606,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_per_rank": per_rank_ms,
+            "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if "float64" in json.dumps(prog["program"]) else "f32",
             "data": "synthetic",

@@ -3,8 +3,9 @@
 
     bin/run_distributed_program.py prog.json cuda -gpus 4 -compare-to-reference [-halo H]
 
-Started once, it launches one process per GPU (torch.distributed.run on 127.0.0.1); started under
-torchrun/mpirun-style launchers that set RANK/WORLD_SIZE it simply runs its rank."""
+Started once, it starts one process per GPU itself (plain subprocesses that find each other over TCP on
+127.0.0.1 -- ``distributed.SocketComm``; no MPI, no torch); started by a launcher that sets RANK / WORLD_SIZE
+(torchrun, mpirun-style wrappers) it simply runs its rank."""
 import argparse
 import os
 import subprocess
@@ -32,10 +33,18 @@ if __name__ == "__main__":
             c = ctypes.c_int(0)
             runtime.load_library().sfb_device_count(ctypes.byref(c))
             n = max(1, c.value)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
-               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500),
-               os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        procs = []
+        for rank in range(n):
+            env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(n), MASTER_ADDR="127.0.0.1",
+                       MASTER_PORT=str(port), SFB200_COMM_PORT=str(port), SFB200_COMM="socket")
+            procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
+        codes = [p.wait() for p in procs]
+        sys.exit(max(codes, key=abs))
     from stencilflow_b200.run_distributed import run_distributed_program
     ret = run_distributed_program(args.stencil_file, args.mode, compare_to_reference=args.compare_to_reference,
                                   input_directory=args.input_directory, halo=args.halo,

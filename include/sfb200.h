@@ -160,6 +160,56 @@ SFB_API int sfb_stream_write_flag(void* stream, void* flag_dptr, uint32_t value)
 /* blocks `stream` (not the host) until *flag >= value. */
 SFB_API int sfb_stream_wait_flag(void* stream, void* flag_dptr, uint32_t value);
 
+/* ---- per-program handle ------------------------------------------------------------------
+ * The counterpart of the trio DaCe generates per program and the reference's driver calls through ctypes:
+ *     __dace_init_<name>(...) -> handle     dace/dace/codegen/compiled_sdfg.py:182-185
+ *     __program_<name>(handle, args...)     dace/dace/codegen/compiled_sdfg.py:286-294
+ *     __dace_exit_<name>(handle)            dace/dace/codegen/compiled_sdfg.py:256-267
+ * Here the library is program-independent, so the handle is *built*: the compiled image, the fields, and
+ * every launch of the plan with a description of its parameters; the library owns the module, the device
+ * memory, the TMA descriptors and the work tables, and a step is one call (sfb_program_run / _call).
+ * A host in any language binds these nine functions and needs nothing else of this header. */
+typedef struct sfb_program sfb_program;
+
+typedef enum sfb_param_kind {
+    SFB_PARAM_BYTES = 0,    /* `size` bytes at `data`, passed by value (scalars, plane ranges) */
+    SFB_PARAM_BUFFER = 1,   /* device address of field `buffer` + `offset` bytes */
+    SFB_PARAM_TMAP = 2,     /* 128-byte tiled TMA descriptor of field `buffer` (+ `offset`), by value */
+    SFB_PARAM_TABLE = 3     /* device address of a copy of the `size` bytes at `data` (work lists) */
+} sfb_param_kind;
+
+typedef struct sfb_launch_param {
+    int32_t kind;
+    int32_t buffer;
+    uint64_t offset;
+    const void* data;
+    uint32_t size;
+    int32_t dtype, rank;            /* SFB_PARAM_TMAP: sfb_dtype, 1..5; dims/box innermost first */
+    uint64_t dims[5];
+    uint64_t strides_bytes[4];
+    uint32_t box[5];
+} sfb_launch_param;
+
+/* Loads the compiled image (cubin from sfb_compile).  *out is NULL on failure. */
+SFB_API int sfb_program_create(const void* image, size_t image_size, sfb_program** out);
+/* Adds a field of `bytes` bytes of device memory; share_with >= 0 places it in the storage of that
+ * earlier field instead (intermediates that are never live together). */
+SFB_API int sfb_program_add_buffer(sfb_program* p, const char* field, size_t bytes, int share_with, int* index);
+SFB_API int sfb_program_buffer(sfb_program* p, const char* field, void** dptr, size_t* bytes);
+/* Appends a launch; parameters are resolved now and kept by the handle. */
+SFB_API int sfb_program_add_launch(sfb_program* p, const char* kernel, const unsigned grid[3], const unsigned block[3],
+                           unsigned dynamic_smem, int num_params, const sfb_launch_param* params);
+SFB_API int sfb_program_clear_launches(sfb_program* p);
+SFB_API int sfb_program_num_launches(sfb_program* p, int* count);
+/* Caller-owned host array of an input (is_output = 0) or output field; NULL unbinds. */
+SFB_API int sfb_program_bind(sfb_program* p, const char* field, void* host_ptr, size_t bytes, int is_output);
+/* All launches, `repetitions` times, on `stream`.  ms_out != NULL: blocks and returns the device time
+ * (CUDA events); ms_out == NULL: asynchronous. */
+SFB_API int sfb_program_run(sfb_program* p, int repetitions, void* stream, float* ms_out);
+/* __program_<name>: bound inputs host->device, all launches, bound outputs device->host; blocking. */
+SFB_API int sfb_program_call(sfb_program* p, void* stream);
+SFB_API int sfb_program_destroy(sfb_program* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@
 #include <sys/mman.h>
 #endif
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -765,6 +766,242 @@ int sfb_stream_write_flag(void* stream, void* flag_dptr, uint32_t value) {
 int sfb_stream_wait_flag(void* stream, void* flag_dptr, uint32_t value) {
     if (!flag_dptr) return fail(SFB_ERR_INVALID, "flag is NULL");
     SFB_DRV(StreamWaitValue32((CUstream)stream, (CUdeviceptr)flag_dptr, value, CU_STREAM_WAIT_VALUE_GEQ));
+    return SFB_OK;
+}
+
+// ---- per-program handle ----------------------------------------------------------------------
+// What DaCe generates per program -- __dace_init_<name> -> handle, __program_<name>(handle, args...),
+// __dace_exit_<name>(handle) (dace/dace/codegen/compiled_sdfg.py:182-185,256-294) -- as one object of this
+// program-independent library: the loaded module, the device fields, every launch of the plan with its
+// parameter block (device pointers, TMA descriptors, work tables patched in here), the caller's host arrays.
+struct sfb_program {
+    struct Buffer {
+        std::string name;
+        void* dptr = nullptr;
+        size_t bytes = 0;
+        int storage = -1;          // index of the buffer that owns the memory (itself if it does)
+        void* host = nullptr;      // bound host array (caller-owned)
+        size_t host_bytes = 0;
+        int is_output = 0;
+    };
+    struct alignas(64) TensorMap { unsigned char bytes[128]; };
+    struct Launch {
+        CUfunction fn = nullptr;
+        unsigned grid[3] = {1, 1, 1}, block[3] = {1, 1, 1}, smem = 0;
+        std::vector<std::vector<unsigned char>> values;    // one entry per parameter (by value)
+        std::vector<TensorMap*> maps;                       // 64-byte aligned descriptors live here
+        std::vector<void*> tables;                          // device memory of work tables
+        std::vector<void*> ptrs;                            // cuLaunchKernel's kernelParams
+    };
+    CUmodule module = nullptr;
+    std::vector<Buffer> buffers;
+    std::vector<Launch*> launches;
+};
+
+static int program_find(sfb_program* p, const char* field) {
+    for (size_t i = 0; i < p->buffers.size(); ++i)
+        if (p->buffers[i].name == field) return (int)i;
+    return -1;
+}
+
+static void program_free_launch(sfb_program::Launch* l) {
+    for (auto* m : l->maps) delete m;
+    for (void* t : l->tables) cudaFree(t);
+    delete l;
+}
+
+int sfb_program_create(const void* image, size_t image_size, sfb_program** out) {
+    (void)image_size;
+    if (!image || !out) return fail(SFB_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = require_init();
+    if (rc != SFB_OK) return rc;
+    CUmodule m = nullptr;
+    SFB_DRV(ModuleLoadData(&m, image));
+    sfb_program* p = new sfb_program();
+    p->module = m;
+    *out = p;
+    return SFB_OK;
+}
+
+int sfb_program_add_buffer(sfb_program* p, const char* field, size_t bytes, int share_with, int* index) {
+    if (!p || !field) return fail(SFB_ERR_INVALID, "NULL argument");
+    if (program_find(p, field) >= 0) return fail(SFB_ERR_INVALID, "field %s was added already", field);
+    sfb_program::Buffer b;
+    b.name = field;
+    b.bytes = bytes;
+    if (share_with >= 0) {
+        if (share_with >= (int)p->buffers.size()) return fail(SFB_ERR_INVALID, "share_with %d out of range", share_with);
+        int owner = p->buffers[share_with].storage;
+        if (p->buffers[owner].bytes < bytes)
+            return fail(SFB_ERR_INVALID, "field %s (%zu bytes) does not fit the storage of %s (%zu bytes)", field, bytes,
+                        p->buffers[owner].name.c_str(), p->buffers[owner].bytes);
+        b.dptr = p->buffers[owner].dptr;
+        b.storage = owner;
+    } else {
+        SFB_CUDA(cudaMalloc(&b.dptr, bytes ? bytes : 1));
+        b.storage = (int)p->buffers.size();
+    }
+    p->buffers.push_back(b);
+    if (index) *index = (int)p->buffers.size() - 1;
+    return SFB_OK;
+}
+
+int sfb_program_buffer(sfb_program* p, const char* field, void** dptr, size_t* bytes) {
+    if (!p || !field) return fail(SFB_ERR_INVALID, "NULL argument");
+    int i = program_find(p, field);
+    if (i < 0) return fail(SFB_ERR_NOT_FOUND, "program has no field %s", field);
+    if (dptr) *dptr = p->buffers[i].dptr;
+    if (bytes) *bytes = p->buffers[i].bytes;
+    return SFB_OK;
+}
+
+int sfb_program_add_launch(sfb_program* p, const char* kernel, const unsigned grid[3], const unsigned block[3],
+                           unsigned dynamic_smem, int num_params, const sfb_launch_param* params) {
+    if (!p || !kernel || !grid || !block || (num_params > 0 && !params)) return fail(SFB_ERR_INVALID, "NULL argument");
+    if (!grid[0] || !grid[1] || !grid[2] || !block[0] || !block[1] || !block[2])
+        return fail(SFB_ERR_INVALID, "empty launch of %s", kernel);
+    int rc = load_driver();
+    if (rc != SFB_OK) return rc;
+    CUfunction f = nullptr;
+    CUresult r = g_drv.ModuleGetFunction(&f, p->module, kernel);
+    if (r == CUDA_ERROR_NOT_FOUND) return fail(SFB_ERR_NOT_FOUND, "kernel %s not found in module", kernel);
+    if (r != CUDA_SUCCESS) return drv_fail("cuModuleGetFunction", r);
+    if (dynamic_smem > 48 * 1024)
+        SFB_DRV(FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dynamic_smem));
+    sfb_program::Launch* l = new sfb_program::Launch();
+    l->fn = f;
+    for (int d = 0; d < 3; ++d) { l->grid[d] = grid[d]; l->block[d] = block[d]; }
+    l->smem = dynamic_smem;
+    l->values.resize(num_params);
+    for (int k = 0; k < num_params; ++k) {
+        const sfb_launch_param& q = params[k];
+        int status = SFB_OK;
+        switch (q.kind) {
+            case SFB_PARAM_BYTES:
+                if (!q.data || !q.size) status = fail(SFB_ERR_INVALID, "parameter %d of %s has no value", k, kernel);
+                else l->values[k].assign((const unsigned char*)q.data, (const unsigned char*)q.data + q.size);
+                break;
+            case SFB_PARAM_BUFFER: {
+                if (q.buffer < 0 || q.buffer >= (int)p->buffers.size()) { status = fail(SFB_ERR_INVALID, "parameter %d of %s: no buffer %d", k, kernel, q.buffer); break; }
+                unsigned char* addr = (unsigned char*)p->buffers[q.buffer].dptr + q.offset;
+                l->values[k].assign((unsigned char*)&addr, (unsigned char*)&addr + sizeof(addr));
+                break;
+            }
+            case SFB_PARAM_TMAP: {
+                if (q.buffer < 0 || q.buffer >= (int)p->buffers.size()) { status = fail(SFB_ERR_INVALID, "parameter %d of %s: no buffer %d", k, kernel, q.buffer); break; }
+                sfb_program::TensorMap* m = new sfb_program::TensorMap();
+                l->maps.push_back(m);
+                status = sfb_tensor_map_tiled(m->bytes, q.dtype, q.rank, (unsigned char*)p->buffers[q.buffer].dptr + q.offset,
+                                              q.dims, q.strides_bytes, q.box, 128);
+                break;
+            }
+            case SFB_PARAM_TABLE: {
+                if (!q.data || !q.size) { status = fail(SFB_ERR_INVALID, "parameter %d of %s has no table", k, kernel); break; }
+                void* t = nullptr;
+                cudaError_t e = cudaMalloc(&t, q.size);
+                if (e == cudaSuccess) e = cudaMemcpy(t, q.data, q.size, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    if (t) cudaFree(t);
+                    status = fail(SFB_ERR_CUDA, "work table of %s: %s", kernel, cudaGetErrorString(e));
+                    break;
+                }
+                l->tables.push_back(t);
+                l->values[k].assign((unsigned char*)&t, (unsigned char*)&t + sizeof(t));
+                break;
+            }
+            default:
+                status = fail(SFB_ERR_INVALID, "parameter %d of %s: unknown kind %d", k, kernel, q.kind);
+        }
+        if (status != SFB_OK) {
+            program_free_launch(l);
+            return status;
+        }
+    }
+    // kernelParams: pointers to the values; tensor maps are passed by value from their aligned storage
+    size_t next_map = 0;
+    for (int k = 0; k < num_params; ++k) {
+        if (params[k].kind == SFB_PARAM_TMAP) l->ptrs.push_back(l->maps[next_map++]->bytes);
+        else l->ptrs.push_back(l->values[k].data());
+    }
+    p->launches.push_back(l);
+    return SFB_OK;
+}
+
+int sfb_program_clear_launches(sfb_program* p) {
+    if (!p) return fail(SFB_ERR_INVALID, "NULL program");
+    for (auto* l : p->launches) program_free_launch(l);
+    p->launches.clear();
+    return SFB_OK;
+}
+
+int sfb_program_num_launches(sfb_program* p, int* count) {
+    if (!p || !count) return fail(SFB_ERR_INVALID, "NULL argument");
+    *count = (int)p->launches.size();
+    return SFB_OK;
+}
+
+int sfb_program_bind(sfb_program* p, const char* field, void* host_ptr, size_t bytes, int is_output) {
+    if (!p || !field) return fail(SFB_ERR_INVALID, "NULL argument");
+    int i = program_find(p, field);
+    if (i < 0) return fail(SFB_ERR_NOT_FOUND, "program has no field %s", field);
+    if (host_ptr && bytes > p->buffers[i].bytes)
+        return fail(SFB_ERR_INVALID, "host array of %s has %zu bytes, the field %zu", field, bytes, p->buffers[i].bytes);
+    p->buffers[i].host = host_ptr;
+    p->buffers[i].host_bytes = host_ptr ? bytes : 0;
+    p->buffers[i].is_output = is_output;
+    return SFB_OK;
+}
+
+int sfb_program_run(sfb_program* p, int repetitions, void* stream, float* ms_out) {
+    if (!p) return fail(SFB_ERR_INVALID, "NULL program");
+    if (repetitions < 1) return fail(SFB_ERR_INVALID, "repetitions must be positive");
+    if (p->launches.empty()) return fail(SFB_ERR_INVALID, "program has no launches");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_out) {
+        SFB_CUDA(cudaEventCreate(&e0));
+        SFB_CUDA(cudaEventCreate(&e1));
+        SFB_CUDA(cudaEventRecord(e0, s));
+    }
+    for (int rep = 0; rep < repetitions; ++rep)
+        for (auto* l : p->launches)
+            SFB_DRV(LaunchKernel(l->fn, l->grid[0], l->grid[1], l->grid[2], l->block[0], l->block[1], l->block[2],
+                                 l->smem, (CUstream)stream, l->ptrs.data(), nullptr));
+    if (ms_out) {
+        SFB_CUDA(cudaEventRecord(e1, s));
+        SFB_CUDA(cudaEventSynchronize(e1));
+        SFB_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return SFB_OK;
+}
+
+int sfb_program_call(sfb_program* p, void* stream) {
+    if (!p) return fail(SFB_ERR_INVALID, "NULL program");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (auto& b : p->buffers)
+        if (b.host && !b.is_output)
+            SFB_CUDA(cudaMemcpyAsync(b.dptr, b.host, b.host_bytes, cudaMemcpyHostToDevice, s));
+    int rc = sfb_program_run(p, 1, stream, nullptr);
+    if (rc != SFB_OK) return rc;
+    for (auto& b : p->buffers)
+        if (b.host && b.is_output)
+            SFB_CUDA(cudaMemcpyAsync(b.host, b.dptr, b.host_bytes, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(cudaStreamSynchronize(s));
+    return SFB_OK;
+}
+
+int sfb_program_destroy(sfb_program* p) {
+    if (!p) return SFB_OK;
+    for (auto* l : p->launches) program_free_launch(l);
+    for (size_t i = 0; i < p->buffers.size(); ++i)
+        if (p->buffers[i].storage == (int)i && p->buffers[i].dptr) cudaFree(p->buffers[i].dptr);
+    if (p->module && load_driver() == SFB_OK) g_drv.ModuleUnload(p->module);
+    delete p;
+    (void)cudaGetLastError();
     return SFB_OK;
 }
 

@@ -86,6 +86,7 @@ class CudaProgram:
         with open(os.path.join(self.cache_dir, "plan.json"), "w") as f:
             json.dump(self.plan.describe(), f, indent=1)
         self.rt = None
+        self.handle = None
         self.module = None
         self.functions = {}
         self.buffers = {}          # field -> DeviceBuffer
@@ -109,6 +110,9 @@ class CudaProgram:
         for l in self.lowered.launches:
             if l.smem > 48 * 1024:
                 self.rt.set_max_dynamic_smem(self.functions[l.kernel], l.smem)
+        # the per-program handle of the C ABI (whole-domain programs; a slab's launches depend on its neighbours)
+        self.handle = self.rt.program_create(self.image) if self.slab is None else None
+        self._handle_index = {}
         self._allocate()
 
     def local_shape(self, field):
@@ -132,9 +136,20 @@ class CudaProgram:
             nbytes = int(np.prod(self.local_shape(name))) * f.data_type.bytes
             storage[sid] = max(storage.get(sid, 0), nbytes)
         ptrs = {}
-        for sid, nbytes in storage.items():
-            ptrs[sid] = self.rt.malloc(nbytes)
-            self._owned.append(ptrs[sid])
+        if self.handle is not None:
+            # whole-domain program: the library's program handle owns the fields (sfb_program_add_buffer)
+            first = {}
+            for name, sid in assign.items():
+                if sid not in first:
+                    first[sid] = self.rt.program_add_buffer(self.handle, name, storage[sid])
+                    self._handle_index[name] = first[sid]
+                else:
+                    self._handle_index[name] = self.rt.program_add_buffer(self.handle, name, storage[sid], first[sid])
+                ptrs[sid] = self.rt.program_buffer(self.handle, name)[0]
+        else:
+            for sid, nbytes in storage.items():
+                ptrs[sid] = self.rt.malloc(nbytes)
+                self._owned.append(ptrs[sid])
         for name, sid in assign.items():
             self.buffers[name] = DeviceBuffer(name, storage[sid], ptrs[sid])
         self.device_bytes = sum(storage.values())
@@ -150,6 +165,9 @@ class CudaProgram:
             self.rt.free(p)
         self._owned, self._tables = [], []
         self.buffers = {}
+        if getattr(self, "handle", None) is not None:
+            self.rt.program_destroy(self.handle)
+            self.handle = None
         if self.module is not None:
             self.rt.module_unload(self.module)
             self.module = None
@@ -175,42 +193,72 @@ class CudaProgram:
     def _build_packs(self):
         s_base, s_begin, s_end = self._slab_range()
         self._packs = [self._pack_launch(l, s_base, s_begin, s_end, push=True) for l in self.lowered.launches]
+        if self.handle is not None:
+            # one library call then runs the whole program: the handle keeps every launch with its parameters
+            self.rt.program_clear_launches(self.handle)
+            for l, fn, grid, pack in self._packs:
+                self._handle_add_launch(l, grid, pack.specs)
 
     def _pack_launch(self, l, s_base, s_begin, s_end, push=False):
         """(launch, function, grid, parameter pack) of launch ``l`` producing planes
         [s_begin, s_end) of the slab axis, device buffers starting at plane ``s_base``.  ``push``: let a
         slab kernel store its edge planes into the neighbouring GPUs' halos (``SlabProgram.execute``
         only; ``push_fn`` is installed by the slab program)."""
-        vals = []
         b0, e0 = l.info.get("range_fn", lambda b, e: (b, e))(s_begin, s_end)
+        specs = self._param_specs(l, s_base, b0, e0, push)
+        vals = []
+        for spec in specs:
+            if spec[0] == "bytes":
+                vals.append(spec[1])
+            elif spec[0] == "buffer":
+                vals.append(ctypes.c_void_p(self.buffers[spec[1]].dptr))
+            elif spec[0] == "tmap":
+                _, field, dt, dims, strides, box = spec
+                vals.append(self.rt.tensor_map(self.buffers[field].dptr, dt, dims, strides, box))
+            elif spec[0] == "table":
+                dptr = self.rt.malloc(spec[1].nbytes)
+                self._tables.append(dptr)
+                self.rt.h2d(dptr, spec[1])
+                self.rt.stream_synchronize()
+                vals.append(ctypes.c_void_p(dptr))
+        pack = rt.pack_params(vals)
+        pack.specs = specs
+        return (l, self.functions[l.kernel], self._grid(l, b0, e0), pack)
+
+    def _grid(self, l, b0, e0):
+        if l.info.get("persistent"):
+            return l.grid_fn(b0, e0, self._resident_ctas(l))
+        return l.grid_fn(b0, e0)
+
+    def _param_specs(self, l, s_base, b0, e0, push=False):
+        """The parameters of launch ``l`` for planes [b0, e0), independent of who launches it:
+        ``("bytes", ctypes value)`` | ``("buffer", field)`` | ``("tmap", field, dtype, dims, strides, box)``
+        | ``("table", int32 array)``."""
+        specs = []
         for a in l.args:
             if a[0] == "buf":
-                vals.append(ctypes.c_void_p(self.buffers[a[1]].dptr))
+                specs.append(("buffer", a[1]))
             elif a[0] == "scalar":
                 dt, name = a[1], a[2]
                 if name not in self.scalar_values:
                     raise KeyError("scalar input {} was not provided".format(name))
-                vals.append(np.ctypeslib.as_ctypes_type(dt.type)(self.scalar_values[name]))
+                specs.append(("bytes", np.ctypeslib.as_ctypes_type(dt.type)(self.scalar_values[name])))
             elif a[0] == "slab":
-                vals += [ctypes.c_int(s_base), ctypes.c_int(b0), ctypes.c_int(e0)]
+                specs += [("bytes", ctypes.c_int(s_base)), ("bytes", ctypes.c_int(b0)), ("bytes", ctypes.c_int(e0))]
             elif a[0] == "int":
-                vals.append(ctypes.c_int(a[1]))
+                specs.append(("bytes", ctypes.c_int(a[1])))
             elif a[0] == "chunk":
-                vals.append(ctypes.c_int(l.info["chunk_fn"](b0, e0)))
+                specs.append(("bytes", ctypes.c_int(l.info["chunk_fn"](b0, e0))))
             elif a[0] == "push":
                 fn_ = getattr(self, "push_fn", None) if push else None
                 d_lo, d_hi, lo_end, hi_begin = fn_(l, a[1]) if fn_ else (0, 0, -(2 ** 31), 2 ** 31 - 1)
-                vals += [ctypes.c_longlong(d_lo), ctypes.c_longlong(d_hi), ctypes.c_int(lo_end), ctypes.c_int(hi_begin)]
+                specs += [("bytes", ctypes.c_longlong(d_lo)), ("bytes", ctypes.c_longlong(d_hi)),
+                          ("bytes", ctypes.c_int(lo_end)), ("bytes", ctypes.c_int(hi_begin))]
             elif a[0] == "worktab":
-                table = np.asarray(l.info["work_fn"](b0, e0, self._resident_ctas(l)), dtype=np.int32)
-                dptr = self.rt.malloc(table.nbytes)
-                self._tables.append(dptr)
-                self.rt.h2d(dptr, table)
-                self.rt.stream_synchronize()
-                vals.append(ctypes.c_void_p(dptr))
+                specs.append(("table", np.ascontiguousarray(
+                    np.asarray(l.info["work_fn"](b0, e0, self._resident_ctas(l)), dtype=np.int32))))
             elif a[0] == "tmap":
                 spec = a[1]
-                buf = self.buffers[spec["field"]]
                 shape = self.local_shape(spec["field"])
                 dt = self.program.fields[spec["field"]].data_type
                 dims = list(reversed(shape))
@@ -219,16 +267,37 @@ class CudaProgram:
                 for d in dims[:-1]:
                     acc *= d
                     strides.append(acc)
-                box = list(spec["box"])
-                vals.append(self.rt.tensor_map(buf.dptr, dt, dims, strides, box))
+                specs.append(("tmap", spec["field"], dt, dims, strides, list(spec["box"])))
             else:
                 raise ValueError(a)
-        pack = rt.pack_params(vals)
-        if l.info.get("persistent"):
-            grid = l.grid_fn(b0, e0, self._resident_ctas(l))
-        else:
-            grid = l.grid_fn(b0, e0)
-        return (l, self.functions[l.kernel], grid, pack)
+        return specs
+
+    def _handle_add_launch(self, l, grid, specs):
+        """The same launch described to the library's program handle (``sfb_program_add_launch``)."""
+        params, keep = [], []
+        for spec in specs:
+            q = rt.LaunchParam()
+            if spec[0] == "bytes":
+                q.kind, q.size = rt.PARAM_BYTES, ctypes.sizeof(spec[1])
+                q.data = ctypes.addressof(spec[1])
+                keep.append(spec[1])
+            elif spec[0] == "buffer":
+                q.kind, q.buffer = rt.PARAM_BUFFER, self._handle_index[spec[1]]
+            elif spec[0] == "tmap":
+                _, field, dt, dims, strides, box = spec
+                q.kind, q.buffer = rt.PARAM_TMAP, self._handle_index[field]
+                q.dtype, q.rank = rt.dtype_code(dt), len(dims)
+                for k, d in enumerate(dims):
+                    q.dims[k] = d
+                    q.box[k] = box[k]
+                for k, st in enumerate(strides):
+                    q.strides_bytes[k] = st
+            elif spec[0] == "table":
+                q.kind, q.size = rt.PARAM_TABLE, spec[1].nbytes
+                q.data = spec[1].ctypes.data
+                keep.append(spec[1])
+            params.append(q)
+        self.rt.program_add_launch(self.handle, l.kernel, grid, l.block, l.smem, params, keep)
 
     def _resident_ctas(self, l):
         """CTA slots of the device for a persistent streamed kernel: SMs x the occupancy the driver
@@ -253,8 +322,11 @@ class CudaProgram:
         if (stream is None and not self._capturing and self.slab is None and len(self._packs) >= 3
                 and self.program.cells <= self.GRAPH_MAX_CELLS and os.environ.get("SFB200_GRAPH", "1") != "0"):
             return self.execute_graph()
-        for l, fn, grid, pack in self._packs:
-            self.rt.launch(fn, grid, l.block, l.smem, pack.array, stream)
+        if self.handle is not None:
+            self.rt.program_run(self.handle, 1, stream)          # all launches in one library call
+        else:
+            for l, fn, grid, pack in self._packs:
+                self.rt.launch(fn, grid, l.block, l.smem, pack.array, stream)
         self.launch_count += len(self._packs)
 
     def execute_graph(self):

@@ -292,6 +292,7 @@ class _FieldInfo:
         self.row_ring = 0             # exchange ring depth (0 = not published)
         self.col_ring = 0
         self.bc = None                # value consumers read outside the domain (None = never read there)
+        self.copy = False             # consumers substitute the centre tap instead (``copy`` boundary)
         self.stored = False
         self.consumed = False
         self.back = 0                 # planes of history a chunk needs before its first output plane
@@ -321,6 +322,7 @@ class GroupAnalysis:
         self.aux_taps: Dict[str, List[Tuple[str, tuple]]] = {}
         self.aux_reach: Dict[str, List[int]] = {}            # name -> [back, fwd] along the streamed dim
         self.aux_bc: Dict[str, float] = {}
+        self.copy_taps = set()                               # (operator, field) read with a ``copy`` boundary
         produced = {op.name for op in ops}
         # fields of the group that operators outside it read: they have to be written to HBM
         later = set()
@@ -360,13 +362,22 @@ class GroupAnalysis:
                 if any((t[1], t[2], t[3]) != (0, 0, 0) for t in taps if t[0] == field):
                     if bc is None:
                         raise NotStreamable("missing boundary condition")
-                    if bc["btype"] == "copy":
-                        raise NotStreamable("copy boundary")
-                    val = float(bc["value"]) if bc["btype"] == "constant" else float(JUNK_VAL)
                     info = self.fields[field]
-                    if info.bc is not None and info.bc != val:
-                        raise NotStreamable("consumers of {} disagree on the boundary value".format(field))
-                    info.bc = val
+                    if bc["btype"] == "copy":
+                        # an out-of-domain tap reads the field's centre tap at the consumer's own cell
+                        # (``intel_fpga.py:179-185,225-227``): decided where the tap is *consumed*, so the
+                        # centre plane has to be in the window and nothing is fixed where the field is produced
+                        if info.bc is not None:
+                            raise NotStreamable("consumers of {} disagree on the boundary handling".format(field))
+                        info.copy = True
+                        self.copy_taps.add((op.name, field))
+                        if (field, 0, 0, 0) not in taps:
+                            taps.append((field, 0, 0, 0))
+                    else:
+                        val = float(bc["value"]) if bc["btype"] == "constant" else float(JUNK_VAL)
+                        if info.copy or (info.bc is not None and info.bc != val):
+                            raise NotStreamable("consumers of {} disagree on the boundary value".format(field))
+                        info.bc = val
             self.taps[op.name] = taps
             info = _FieldInfo(op.name, "op", op.data_type)
             info.stored = (program.fields[op.name].kind == "output") or (op.name in later)
@@ -934,6 +945,9 @@ class StreamKernelGen:
         e("#pragma unroll 1")
         e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
         needs_bc = [i for i in a.fields.values() if self._needs_fixup(i)]
+        # ``copy`` boundaries are resolved by the consuming operator: its trips near the border need the code too
+        needs_bc += [a.fields[op] for (op, _) in sorted(a.copy_taps) if a.fields[op] not in needs_bc]
+        needs_bc += [a.fields[f] for (_, f) in sorted(a.copy_taps) if a.fields[f] not in needs_bc]
         variants = [True]
         if needs_bc and self.fast_path:
             # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no
@@ -1311,8 +1325,7 @@ class StreamKernelGen:
             age = info.lag - d - src.lag
             return (t.field, age, r + dj), dk
 
-        def tap_cell(t: ex.Tap, r: int, c: int) -> str:
-            """C expression of the cell at column c (relative to the thread's first cell)"""
+        def raw_cell(t: ex.Tap, r: int, c: int) -> str:
             key, _ = tap_key(t, r)
             vec, tag = names[key]
             nl, nr = rows[key]
@@ -1321,6 +1334,31 @@ class StreamKernelGen:
             if c < 0:
                 return "l_{}[{}]".format(tag, nl + c)
             return "g_{}[{}]".format(tag, c - V)
+
+        copy_fields = {f for (o, f) in a.copy_taps if o == op.name} if self.with_bc else set()
+
+        def tap_cell(t: ex.Tap, r: int, c: int) -> str:
+            """C expression of the cell at column c (relative to the thread's first cell); a ``copy`` tap
+            that leaves the domain reads the field's centre tap at the cell being computed instead"""
+            text = raw_cell(t, r, c)
+            if t.field not in copy_fields:
+                return text
+            if a.ndim == 3:
+                d, dj, dk = t.offset
+            else:
+                d, dj, dk = t.offset[1], 0, t.offset[2]
+            if (d, dj, dk) == (0, 0, 0):
+                return text
+            v = c - dk                                   # the cell of this thread being computed
+            conds = []
+            if d:
+                conds.append("(unsigned)(({}) + ({})) < {}u".format(plane, d, self.NS))
+            if dj:
+                conds.append("(unsigned)(gj0 + ({})) < {}u".format(r + dj, self.NJ))
+            if dk:
+                conds.append("(unsigned)(gk + ({})) < {}u".format(c, self.NK))
+            centre = raw_cell(ex.Tap(t.field, (0, 0, 0)), r, v)
+            return "(({}) ? {} : {})".format(" && ".join(conds), text, centre)
 
         # lower-dimensional inputs: taps that vary along the streamed dimension are loaded per plane
         self.aux_cur = {}
@@ -1435,7 +1473,9 @@ class StreamKernelGen:
                         key, dk = tap_key(x, r)
                         vec, tag = names[key]
                         c = 2 * h + dk
-                        if dk % 2 == 0 and 0 <= c and c + 1 < V:
+                        plain = not (self.with_bc and (op.name, x.field) in self.ana.copy_taps
+                                     and any(x.offset))
+                        if plain and dk % 2 == 0 and 0 <= c and c + 1 < V:
                             return ("p", "{}[{}]".format(vec, c // 2))
                         return ("s", tap_cell(x, r, c), tap_cell(x, r, c + 1))
                     if isinstance(x, ex.Bin):

@@ -22,7 +22,7 @@ def run_distributed_program(stencil_file, mode="cuda", compare_to_reference=Fals
         raise ValueError("Unrecognized execution mode: {}".format(mode))
     if isinstance(log_level, int):
         log_level = LogLevel(log_level)
-    comm = comm or distributed.TorchComm("gloo")
+    comm = comm or distributed.make_comm()
     rank, world = comm.rank, comm.world
     verbose = log_level >= LogLevel.BASIC
     description = helper.parse_json(stencil_file)

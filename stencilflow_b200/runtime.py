@@ -44,6 +44,24 @@ _vp = ctypes.c_void_p
 _vpp = ctypes.POINTER(ctypes.c_void_p)
 _u3 = ctypes.c_uint * 3
 
+PARAM_BYTES, PARAM_BUFFER, PARAM_TMAP, PARAM_TABLE = 0, 1, 2, 3
+
+
+class LaunchParam(ctypes.Structure):
+    """``sfb_launch_param`` (include/sfb200.h)."""
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("buffer", ctypes.c_int32),
+        ("offset", ctypes.c_uint64),
+        ("data", ctypes.c_void_p),
+        ("size", ctypes.c_uint32),
+        ("dtype", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("dims", ctypes.c_uint64 * 5),
+        ("strides_bytes", ctypes.c_uint64 * 4),
+        ("box", ctypes.c_uint32 * 5),
+    ]
+
 # name -> (restype, argtypes); the table doubles as the list the CPU tests check against sfb200.h
 PROTOTYPES = {
     "sfb_abi_version": (ctypes.c_int, []),
@@ -106,6 +124,18 @@ PROTOTYPES = {
     "sfb_enable_peer_access": (ctypes.c_int, [ctypes.c_int]),
     "sfb_stream_write_flag": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32]),
     "sfb_stream_wait_flag": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32]),
+    "sfb_program_create": (ctypes.c_int, [_vp, ctypes.c_size_t, _vpp]),
+    "sfb_program_add_buffer": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_int)]),
+    "sfb_program_buffer": (ctypes.c_int, [_vp, ctypes.c_char_p, _vpp, ctypes.POINTER(ctypes.c_size_t)]),
+    "sfb_program_add_launch": (ctypes.c_int, [_vp, ctypes.c_char_p, _u3, _u3, ctypes.c_uint, ctypes.c_int,
+                                              ctypes.POINTER(LaunchParam)]),
+    "sfb_program_clear_launches": (ctypes.c_int, [_vp]),
+    "sfb_program_num_launches": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
+    "sfb_program_bind": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "sfb_program_run": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "sfb_program_call": (ctypes.c_int, [_vp, _vp]),
+    "sfb_program_destroy": (ctypes.c_int, [_vp]),
 }
 
 _lib = None
@@ -354,6 +384,57 @@ class Runtime:
         _check(self.lib.sfb_compare(_vp(ref_dptr), _vp(res_dptr), n, dtype_code(dtype), tolerance,
                                     ctypes.byref(m), ctypes.byref(bad)))
         return m.value, bad.value
+
+    # -- per-program handle (sfb_program_*: module, fields, launches and their parameters live in the library)
+    def program_create(self, image):
+        buf = ctypes.create_string_buffer(image, len(image))
+        h = _vp()
+        _check(self.lib.sfb_program_create(buf, len(image), ctypes.byref(h)))
+        return h
+
+    def program_add_buffer(self, handle, field, nbytes, share_with=-1):
+        idx = ctypes.c_int(-1)
+        _check(self.lib.sfb_program_add_buffer(handle, field.encode(), int(nbytes), int(share_with), ctypes.byref(idx)))
+        return idx.value
+
+    def program_buffer(self, handle, field):
+        p, n = _vp(), ctypes.c_size_t(0)
+        _check(self.lib.sfb_program_buffer(handle, field.encode(), ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def program_add_launch(self, handle, kernel, grid, block, smem, params, keep):
+        """``params``: list of LaunchParam; ``keep``: objects the params point into (alive for the call)."""
+        arr = (LaunchParam * max(1, len(params)))(*params)
+        _check(self.lib.sfb_program_add_launch(handle, kernel.encode(), _u3(*grid), _u3(*block), int(smem),
+                                               len(params), arr))
+
+    def program_clear_launches(self, handle):
+        _check(self.lib.sfb_program_clear_launches(handle))
+
+    def program_num_launches(self, handle):
+        n = ctypes.c_int(0)
+        _check(self.lib.sfb_program_num_launches(handle, ctypes.byref(n)))
+        return n.value
+
+    def program_bind(self, handle, field, arr, is_output):
+        if arr is None:
+            _check(self.lib.sfb_program_bind(handle, field.encode(), None, 0, int(is_output)))
+        else:
+            assert arr.flags["C_CONTIGUOUS"]
+            _check(self.lib.sfb_program_bind(handle, field.encode(), _vp(arr.ctypes.data), arr.nbytes, int(is_output)))
+
+    def program_run(self, handle, repetitions=1, stream=None, timed=False):
+        """All launches ``repetitions`` times in one call; ``timed``: blocks and returns the device time (ms)."""
+        ms = ctypes.c_float(0)
+        _check(self.lib.sfb_program_run(handle, int(repetitions), self.stream if stream is None else stream,
+                                        ctypes.byref(ms) if timed else None))
+        return ms.value if timed else None
+
+    def program_call(self, handle, stream=None):
+        _check(self.lib.sfb_program_call(handle, self.stream if stream is None else stream))
+
+    def program_destroy(self, handle):
+        _check(self.lib.sfb_program_destroy(handle))
 
     # -- multi-GPU
     def ipc_get_handle(self, dptr):

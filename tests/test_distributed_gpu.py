@@ -35,6 +35,19 @@ def _run_group(cmd, env, timeout):
         return (out or "") + "\n[timeout after {} s: process group killed]".format(timeout), -9
 
 
+def _results(out):
+    """Every ``RESULT {json}`` record in the merged output of the ranks (two ranks finishing together may
+    share a line)."""
+    dec, found, at = json.JSONDecoder(), [], 0
+    while True:
+        at = out.find("RESULT {", at)
+        if at < 0:
+            return found
+        obj, end = dec.raw_decode(out, at + len("RESULT "))
+        found.append(obj)
+        at = end
+
+
 @pytest.mark.parametrize("name,fuse", [
     ("ref_jacobi3d_32x32x32_8itr_8vec", True),
     ("ref_jacobi3d_32x32x32_8itr_8vec", False),
@@ -75,7 +88,7 @@ def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
         env["SFB200_PIPELINE_PIECES"] = "4"         # 88 planes per rank: pieces of 22 planes
     out, code = _run_group(cmd, env, 240)
     assert code == 0, out[-4000:]
-    lines = [json.loads(l[len("RESULT "):]) for l in out.splitlines() if l.startswith("RESULT ")]
+    lines = _results(out)
     assert len(lines) == 2 and all(l["ok"] for l in lines)
     if name.startswith("chain3d") and "SFB200_MAX_DEPTH" not in env:
         # wide halo (accumulated reach 8) -> the host-array call ran as the overlapped exchange-free schedule
@@ -83,3 +96,31 @@ def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if name.startswith("upwind3d"):
         assert sorted(l["sends"] for l in lines) != [0, 0]          # the halo really was exchanged
         assert min(l["sends"] for l in lines) == 0                  # ... by one side only
+
+
+
+@pytest.mark.parametrize("name,halo", [("ref_jacobi3d_32x32x32_8itr_8vec", 0), ("hdiff_24x28x16", 2)])
+def test_run_distributed_program_cli(native_lib, name, halo, tmp_path):
+    """``bin/run_distributed_program.py prog.json cuda -gpus 2 -compare-to-reference``: the command line starts
+    its own ranks (TCP rendezvous, no torchrun), the last rank verifies against the CPU program and the
+    exit code says so (reference bin/run_distributed_program.py:283-341)."""
+    if _gpu_count(native_lib) < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import program_path
+    cmd = [sys.executable, os.path.join(ROOT, "bin", "run_distributed_program.py"), program_path(name), "cuda",
+           "-gpus", "2", "-compare-to-reference", "-halo", str(halo), "-repetitions", "2",
+           "-input-directory", os.path.dirname(program_path(name))]
+    env = dict(os.environ, SFB200_MAX_DEPTH="4")
+    env.pop("RANK", None)
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                            start_new_session=True, cwd=str(tmp_path))
+    try:
+        out, _ = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, _ = proc.communicate()
+        raise AssertionError("timeout\n" + (out or "")[-3000:])
+    assert proc.returncode == 0, out[-4000:]
+    assert "Results verified." in out and "halo pushes per execution" in out
+    assert os.path.isdir(tmp_path / "results" / name)

@@ -533,3 +533,42 @@ def test_exported_program_conventions_end_to_end(gpu, tmp_path, monkeypatch):
     got, prog_obj = _run_cuda(name, inputs)
     _check(name, got, expected)
     assert [l.family for l in prog_obj.lowered.launches] == ["streamed"]          # one fused pass
+
+
+@pytest.mark.parametrize("name,opts", [("ref_jacobi3d_32x32x32_8itr_8vec", dict(max_depth=4)),
+                                       ("ref_jacobi3d_32x32x32_8itr_8vec", dict(fuse=False)),
+                                       ("hdiff_24x28x16", dict(max_depth=4)),
+                                       ("jacobi2d_96x128_6itr_shrink_f64", dict(max_depth=3))])
+def test_program_handle_round_trip(gpu, name, opts):
+    """The per-program handle of the C ABI (``sfb_program_create / add_buffer / add_launch / bind / call /
+    run / destroy``, the counterpart of DaCe's ``__dace_init / __program / __dace_exit``): host arrays are
+    bound once, one library call copies in, runs every launch and copies out -- compared with the oracle;
+    ``sfb_program_run`` then repeats the launches and reports the device time."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    inputs = random_inputs(name, seed=23)
+    expected = rn.run_reference(program_path(name), inputs)
+    prog = CudaProgram(program_path(name), plan_options=PlanOptions(**opts))
+    assert prog.handle is not None
+    prog.set_scalars({k: v for k, v in inputs.items() if getattr(v, "ndim", 0) == 0})
+    prog._build_packs()
+    rtm = prog.rt
+    assert rtm.program_num_launches(prog.handle) == len(prog.lowered.launches)
+    outs = {}
+    for field, f in prog.program.fields.items():
+        if f.is_scalar:
+            continue
+        if f.kind == "input":
+            rtm.program_bind(prog.handle, field, np.ascontiguousarray(inputs[field]), 0)
+        elif f.kind == "output":
+            outs[field] = np.zeros(f.shape, dtype=f.data_type.type)
+            rtm.program_bind(prog.handle, field, outs[field], 1)
+    rtm.program_call(prog.handle)
+    _check(name, outs, expected)
+    ms = rtm.program_run(prog.handle, 3, timed=True)
+    assert ms > 0.0
+    # the fields the handle owns are the ones the Python object reports
+    for field, buf in prog.buffers.items():
+        assert rtm.program_buffer(prog.handle, field)[0] == buf.dptr
+    prog.close()
