@@ -6,14 +6,14 @@ TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 for c in 1 2 3; do
-  timeout 900 python bench.py --config $c --steps 10 --warmup 3 > $OUT/${TAG}_config${c}_bench.json 2> $OUT/${TAG}_config${c}_bench.err
+  timeout 900 python bench.py --config $c --steps 20 --warmup 3 --no-strong > $OUT/${TAG}_config${c}_bench.json 2> $OUT/${TAG}_config${c}_bench.err
   tail -c 600 $OUT/${TAG}_config${c}_bench.json; echo
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
       --log-file $OUT/${TAG}_config${c}_launches.csv \
-      python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+      python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-strong --no-verify > /dev/null 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:sf_ -s 3 -c 1 \
       -o $OUT/${TAG}_config${c}_full -f \
-      python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+      python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-strong --no-verify > /dev/null 2>&1
   ALG=$(python -c "import json;print(json.load(open('$OUT/${TAG}_config${c}_bench.json'))['roofline']['algorithmic_bytes_per_launch'])")
   python scripts/ncu_summary.py $OUT/${TAG}_config${c}_full.ncu-rep $ALG > $OUT/${TAG}_config${c}_ncu_full_summary.txt
   python scripts/ncu_source.py $OUT/${TAG}_config${c}_full.ncu-rep --top 16 >> $OUT/${TAG}_config${c}_ncu_full_summary.txt

@@ -299,6 +299,60 @@ class CudaProgram:
             params.append(q)
         self.rt.program_add_launch(self.handle, l.kernel, grid, l.block, l.smem, params, keep)
 
+    def export_plan(self, directory, inputs=None):
+        """Writes what a host in another language needs to run this program through the per-program
+        handle of the C ABI (``sfb_program_*``): ``kernel.cubin``, ``program.sfbplan`` (fields, launches
+        with their parameters, input/output files) and, if ``inputs`` are given, the raw ``.dat`` input
+        arrays.  ``examples/run_sfbplan.c`` is such a host.  Needs a device (the grids of persistent
+        kernels depend on its occupancy).  Returns the path of the plan script."""
+        if self.slab is not None:
+            raise ValueError("a slab program is driven by its rank, not by a plan script")
+        if inputs:
+            self.set_scalars({k: v for k, v in inputs.items() if self.program.fields[k].is_scalar})
+        if self._packs is None:
+            self._build_packs()
+        os.makedirs(directory, exist_ok=True)
+        with open(os.path.join(directory, "kernel.cubin"), "wb") as f:
+            f.write(self.image)
+        names = list(self._handle_index)
+        order = sorted(names, key=lambda n: self._handle_index[n])
+        assign = self.plan.buffer_assignment()
+        first = {}
+        lines = ["image {}".format(os.path.join(directory, "kernel.cubin"))]
+        for name in order:
+            sid = assign[name]
+            share = first.get(sid, -1)
+            first.setdefault(sid, self._handle_index[name])
+            lines.append("buffer {} {} {}".format(name, self.buffers[name].nbytes, share))
+        for l, fn, grid, pack in self._packs:
+            lines.append("launch {} {} {} {} {} {} {} {} {}".format(l.kernel, *grid, *l.block, l.smem, len(pack.specs)))
+            for spec in pack.specs:
+                if spec[0] == "bytes":
+                    raw = bytes(spec[1])
+                    lines.append("  bytes {} {}".format(len(raw), raw.hex()))
+                elif spec[0] == "buffer":
+                    lines.append("  buffer {} 0".format(self._handle_index[spec[1]]))
+                elif spec[0] == "tmap":
+                    _, field, dt, dims, strides, box = spec
+                    lines.append("  tmap {} {} {} {}".format(self._handle_index[field], rt.dtype_code(dt), len(dims),
+                                                             " ".join(map(str, list(dims) + list(strides) + list(box)))))
+                elif spec[0] == "table":
+                    lines.append("  table {} {}".format(spec[1].size, " ".join(map(str, spec[1].tolist()))))
+        for name, f in self.program.fields.items():
+            if f.is_scalar or f.kind == "intermediate":
+                continue
+            path = os.path.join(directory, name + ".dat")
+            if f.kind == "input":
+                if inputs is not None and name in inputs:
+                    np.ascontiguousarray(np.asarray(inputs[name], dtype=f.data_type.type)).tofile(path)
+                lines.append("input {} {}".format(name, path))
+            else:
+                lines.append("output {} {}".format(name, path))
+        script = os.path.join(directory, "program.sfbplan")
+        with open(script, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        return script
+
     def _resident_ctas(self, l):
         """CTA slots of the device for a persistent streamed kernel: SMs x the occupancy the driver
         reports for the loaded function (one CTA per slot streams an equal share of the pass)."""

@@ -383,3 +383,57 @@ def to_source(e: Expr, tap: Optional[Callable[[Tap], str]] = None) -> str:
             return "{}({})".format(x.fn, ", ".join(go(a) for a in x.args))
         raise TypeError(type(x))
     return go(e)
+
+
+def pair_odd_taps(e: Expr, balance: bool = False) -> Expr:
+    """Re-associates sums so that the taps with an odd innermost offset are added to each other first:
+    ``((((a[i-1] + a[i+1]) + a[j-1]) + a[j+1]) + a[k-1]) + a[k+1]`` becomes
+    ``(((a[i-1] + a[i+1]) + a[j-1]) + a[j+1]) + (a[k-1] + a[k+1])``.
+
+    Why: the float32 kernels compute on aligned *pairs* of neighbouring k-cells (``add.f32x2``); a tap with
+    an odd k-offset straddles two pairs, so adding it to a packed running sum costs two scalar additions.
+    Adding the straddling taps to each other first costs two scalar additions per tap but one, and a single
+    packed addition for the lot -- one issue slot in eight less for a 7-point stencil.  Both kernel
+    families are lowered from the rewritten tree, so fused and one-operator results stay bit-identical;
+    against the reference the change is an admissible re-association (its CPU program is built with
+    ``-ffast-math``, ``dace/dace/config_schema.yml:272``) well inside the 1e-5 tolerance.
+
+    ``balance``: the sums are built as balanced trees instead of left-to-right chains -- a shorter dependent
+    chain per cell (``(a + b) + (c + d)``: two additions deep instead of three), which is what a
+    latency-bound float64 kernel with two warps per scheduler needs."""
+    if isinstance(e, Bin):
+        if e.op == "+":
+            terms = []
+            node = e
+            while isinstance(node, Bin) and node.op == "+":
+                terms.append(node.b)
+                node = node.a
+            terms.append(node)
+            terms = [pair_odd_taps(t, balance) for t in reversed(terms)]
+            odd = [t for t in terms if isinstance(t, Tap) and t.offset[2] is not None and t.offset[2] % 2 != 0]
+
+            def chain(ts):
+                if balance and len(ts) > 2:
+                    half = (len(ts) + 1) // 2
+                    return Bin("+", chain(ts[:half]), chain(ts[half:]))
+                acc = ts[0]
+                for t in ts[1:]:
+                    acc = Bin("+", acc, t)
+                return acc
+
+            if len(odd) >= 2 and len(odd) < len(terms):
+                rest = [t for t in terms if not any(t is o for o in odd)]
+                return Bin("+", chain(rest), chain(odd))
+            return chain(terms)
+        return Bin(e.op, pair_odd_taps(e.a, balance), pair_odd_taps(e.b, balance))
+    if isinstance(e, Neg):
+        return Neg(pair_odd_taps(e.a, balance))
+    if isinstance(e, Cmp):
+        return Cmp(e.op, pair_odd_taps(e.a, balance), pair_odd_taps(e.b, balance))
+    if isinstance(e, Logic):
+        return Logic(e.op, [pair_odd_taps(a, balance) for a in e.args])
+    if isinstance(e, Select):
+        return Select(pair_odd_taps(e.cond, balance), pair_odd_taps(e.a, balance), pair_odd_taps(e.b, balance))
+    if isinstance(e, Call):
+        return Call(e.fn, [pair_odd_taps(a, balance) for a in e.args])
+    return e

@@ -10,10 +10,12 @@ In the reference every operator is distilled to
 """
 
 import collections
+import os
 from typing import Dict, List, Optional, Tuple
 
 import networkx as nx
 
+from . import dtypes
 from . import expr as ex
 from .base_node_class import Input, Output
 from .kernel import Kernel
@@ -213,10 +215,17 @@ def make_program(chain) -> StencilProgram:
                     bcs[field] = _normalise_bc(node.boundary_conditions[field], field, node.name)
                 except ValueError:
                     pass
+        statements = node.statements
+        mode = os.environ.get("SFB200_REASSOCIATE", "1")
+        if mode != "0" and node.data_type in (dtypes.float32, dtypes.float64):
+            # float32 kernels compute on pairs of k-neighbours: taps that straddle two pairs are summed first.
+            # float64 kernels are latency-bound: their sums become balanced trees (mode 2: float32 too).
+            balance = node.data_type == dtypes.float64 or mode == "2"
+            statements = [ex.Statement(st.target, ex.pair_odd_taps(st.value, balance)) for st in statements]
         ops.append(StencilOp(
             name=node.name, shape=shape, iterators=iterators, accesses=accesses,
             output_fields={node.name: [0] * len(shape)}, boundary_conditions=bcs,
-            code=node.kernel_string, statements=node.statements, data_type=node.data_type,
+            code=node.kernel_string, statements=statements, data_type=node.data_type,
             scalars=scalars))
     for out in chain.outputs:
         if out not in fields or fields[out].kind != "output":

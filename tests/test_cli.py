@@ -65,3 +65,18 @@ def test_cuda_mode_fails_loudly_without_a_device(native_lib, tmp_path):
                 "-compare-to-reference"], cwd=str(tmp_path))
     assert res.returncode != 0
     assert "NO_DEVICE" in res.stdout or "no usable GPU" in res.stdout or "CUDA" in res.stdout
+
+
+def test_plain_c_host_example_builds(native_lib, tmp_path):
+    """examples/run_sfbplan.c needs nothing but include/sfb200.h and libsfb200.so."""
+    from stencilflow_b200 import runtime
+    libdir = os.path.dirname(runtime.LIB_PATH)
+    exe = str(tmp_path / "run_sfbplan")
+    res = subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "examples", "run_sfbplan.c"), "-o", exe, "-L", libdir, "-lsfb200",
+                          "-Wl,-rpath," + libdir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 2 and "usage" in res.stdout
+    out = subprocess.run(["ldd", exe], stdout=subprocess.PIPE, text=True).stdout
+    assert "libsfb200" in out and "python" not in out.lower() and "torch" not in out.lower()

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, HALO, all_programs, program_path, random_inputs
+from conftest import GOLDEN, HALO, ROOT, all_programs, program_path, random_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -572,3 +572,33 @@ def test_program_handle_round_trip(gpu, name, opts):
     for field, buf in prog.buffers.items():
         assert rtm.program_buffer(prog.handle, field)[0] == buf.dptr
     prog.close()
+
+
+@pytest.mark.parametrize("name,opts", [("ref_jacobi3d_32x32x32_8itr_8vec", dict(max_depth=4)),
+                                       ("hdiff_24x28x16", dict(max_depth=4)),
+                                       ("ref_varying_dimensionality", dict(fuse=False))])
+def test_plain_c_host_runs_the_program_handle(gpu, name, opts, tmp_path):
+    """No Python in the process that computes: ``examples/run_sfbplan.c`` (gcc, links libsfb200.so only)
+    builds the per-program handle from an exported plan script, runs it and writes the outputs, which
+    must match the oracle -- the C ABI is bindable from any language, as DaCe's init/program/exit trio is."""
+    import subprocess
+    from oracle import reference_numpy as rn
+    from stencilflow_b200 import runtime
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    exe = str(tmp_path / "run_sfbplan")
+    libdir = os.path.dirname(runtime.LIB_PATH)
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "run_sfbplan.c"),
+                    "-o", exe, "-L", libdir, "-lsfb200", "-Wl,-rpath," + libdir], check=True)
+    inputs = random_inputs(name, seed=29)
+    expected = rn.run_reference(program_path(name), inputs)
+    prog = CudaProgram(program_path(name), plan_options=PlanOptions(**opts))
+    script = prog.export_plan(str(tmp_path / "plan"), inputs)
+    shapes = {o: (prog.program.fields[o].shape, prog.program.fields[o].data_type.type) for o in prog.program.outputs}
+    prog.close()
+    res = subprocess.run([exe, script, "0", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout
+    assert "launch(es), 3 repetitions" in res.stdout
+    got = {o: np.fromfile(str(tmp_path / "plan" / (o + ".dat")), dtype=dt).reshape(shape)
+           for o, (shape, dt) in shapes.items()}
+    _check(name, got, expected)

@@ -37,7 +37,10 @@ def _simulate(path):
 
 
 # the 32^3 x 8 chains take ~10 s each in pure Python: one of them is enough
-FAST_CASES = [c for c in sorted(REFERENCE_SIM) if c != "ref_jacobi3d_32x32x32_8itr_8vec_rand"]
+# (cases the reference ran in an equivalent, transformed form -- shrink as a constant, 2-D embedded in 3-D,
+# statements inlined -- have other cycle counts than the original program: they pin the oracle, not this model)
+FAST_CASES = [c for c in sorted(REFERENCE_SIM)
+              if c != "ref_jacobi3d_32x32x32_8itr_8vec_rand" and "transforms" not in REFERENCE_SIM[c]]
 
 
 @pytest.mark.parametrize("case", FAST_CASES)
