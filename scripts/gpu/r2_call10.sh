@@ -9,6 +9,10 @@ B="timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-e2e --no-strong
 for r in 1 0 1 0; do
   SFB200_REASSOCIATE=$r $B --config 1 >> ${O}_cfg1_reassoc$r.json 2>> ${O}_cfg1_reassoc$r.err
 done
+SFB200_REASSOCIATE=2 $B --config 1 > ${O}_cfg1_reassoc2.json 2> ${O}_cfg1_reassoc2.err
+for r in 1 0 1 0; do
+  SFB200_REASSOCIATE=$r $B --config 3 >> ${O}_cfg3_reassoc$r.json 2>> ${O}_cfg3_reassoc$r.err
+done
 SFB200_REASSOCIATE=0 $B --config 2 > ${O}_cfg2_reassoc0.json 2> ${O}_cfg2_reassoc0.err
 SFB200_REASSOCIATE=1 $B --config 2 > ${O}_cfg2_reassoc1.json 2> ${O}_cfg2_reassoc1.err
 python - <<'PY'

@@ -85,18 +85,33 @@ def hdiff_jki(shape, dtype="float32"):
 
 
 def programs_dir():
+    """``programs/`` of the repository: the JSON of the BASELINE.json configurations (tracked)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    d = os.environ.get("SFB200_PROGRAMS", os.path.join(root, "programs"))
+    return os.environ.get("SFB200_PROGRAMS", os.path.join(root, "programs"))
+
+
+def scratch_dir():
+    """Where generated programs that are not one of the tracked configurations go (weak-scaled domains,
+    test chains): next to the compiled-kernel cache."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(os.environ.get("SFB200_CACHE", os.path.join(root, ".sfcache")), "programs")
     os.makedirs(d, exist_ok=True)
     return d
 
 
 def write_program(prog, name, directory=None):
-    path = os.path.join(directory or programs_dir(), name + ".json")
+    """Writes ``prog`` as ``<name>.json`` and returns the path: into ``directory`` if given, over the
+    tracked file of that name in ``programs/`` if there is one, else into the scratch directory."""
+    if directory is None:
+        tracked = os.path.join(programs_dir(), name + ".json")
+        directory = programs_dir() if os.path.isfile(tracked) else scratch_dir()
+    path = os.path.join(directory, name + ".json")
     text = json.dumps(prog, indent=1)
     if not os.path.isfile(path) or open(path).read() != text:
-        with open(path, "w") as f:
+        tmp = path + ".tmp{}".format(os.getpid())
+        with open(tmp, "w") as f:
             f.write(text)
+        os.replace(tmp, path)
     return path
 
 
