@@ -650,9 +650,7 @@ class StreamKernelGen:
         self.with_bc = True
         self._tmp = 0
         # how produced planes get their out-of-domain cells set to the boundary value (see _finish_field)
-        self.bc_mode = os.environ.get("SFB200_BC_MODE", "thread")
-        if self.bc_mode not in ("thread", "cta"):
-            self.bc_mode = "thread"
+        self.bc_mode = os.environ.get("SFB200_BC_MODE", "auto")
         # persistent scheduling (see schedule_work): tiles of the in-plane grid
         # slab mode: the kernel stores the edge planes of its results a second time, straight into the
         # neighbouring GPUs' halo planes (peer stores over NVLink), instead of leaving them to a copy
@@ -663,6 +661,11 @@ class StreamKernelGen:
         if persistent is None:
             persistent = persistent_default(self.n_tiles, SM_COUNT * resident_estimate(geo))
         self.persistent = bool(persistent)
+        if self.bc_mode not in ("thread", "cta"):
+            # per-thread fix-ups pay off where domain-edge tiles would hold up the others (many tiles, persistent
+            # CTAs: Jacobi-3D 1024^3 4.17 -> 4.05 ms); their extra code costs registers the kernels with few,
+            # long-running tiles do not have to spare (hdiff: 123 -> 128 registers and a spill, 0.163 -> 0.180 ms)
+            self.bc_mode = "thread" if self.persistent else "cta"
 
     # ------------------------------------------------------------------ unrolling
     def _choose_unroll(self, cap):
@@ -1096,21 +1099,29 @@ class StreamKernelGen:
 
             # one in-domain bit per owned cell.  "thread": only warps that own cells outside the domain
             # (or a plane outside it) enter, and a thread whose cells are all outside overwrites them
-            # without testing each one; "cta": every warp of a tile that has any such cell does
-            cond = "cmask == {}u".format(full) if self.bc_mode == "thread" else "interior"
-            e("if (!(pin && {})) {{".format(cond), 3)
-            e("const u32 m = pin ? cmask : 0u;", 4)
-            e("if (m == 0u) {", 4)
-            for r in range(R):
-                for v in range(V):
-                    fix(r, v, 5)
-            e("} else {", 4)
-            for r in range(R):
-                for v in range(V):
-                    e("if (!((m >> {b}) & 1u)) {c} = {bc};".format(
-                        b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=bc), 5)
-            e("}", 4)
-            e("}", 3)
+            # without testing each one; "cta": every warp of a tile that has any such cell tests every cell
+            if self.bc_mode == "thread":
+                e("if (!(pin && cmask == {}u)) {{".format(full), 3)
+                e("const u32 m = pin ? cmask : 0u;", 4)
+                e("if (m == 0u) {", 4)
+                for r in range(R):
+                    for v in range(V):
+                        fix(r, v, 5)
+                e("} else {", 4)
+                for r in range(R):
+                    for v in range(V):
+                        e("if (!((m >> {b}) & 1u)) {c} = {bc};".format(
+                            b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=bc), 5)
+                e("}", 4)
+                e("}", 3)
+            else:
+                e("if (!(pin && interior)) {", 3)
+                e("const u32 m = pin ? cmask : 0u;", 4)
+                for r in range(R):
+                    for v in range(V):
+                        e("if (!((m >> {b}) & 1u)) {c} = {bc};".format(
+                            b=r * V + v, c=self.cellref("nv[{}]".format(r), v), bc=bc), 4)
+                e("}", 3)
             e("}")
         if info.row_ring and info.name not in g.direct:
             n = info.row_reach

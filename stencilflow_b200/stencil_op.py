@@ -217,11 +217,12 @@ def make_program(chain) -> StencilProgram:
                     pass
         statements = node.statements
         mode = os.environ.get("SFB200_REASSOCIATE", "1")
-        if mode != "0" and node.data_type in (dtypes.float32, dtypes.float64):
-            # float32 kernels compute on pairs of k-neighbours: taps that straddle two pairs are summed first.
-            # float64 kernels are latency-bound: their sums become balanced trees (mode 2: float32 too).
-            balance = node.data_type == dtypes.float64 or mode == "2"
-            statements = [ex.Statement(st.target, ex.pair_odd_taps(st.value, balance)) for st in statements]
+        if mode in ("1", "2") and node.data_type == dtypes.float32 or mode == "3" and node.data_type == dtypes.float64:
+            # float32 kernels compute on pairs of k-neighbours: taps that straddle two pairs are summed first
+            # (fewer instructions; measured time-neutral on the Jacobi-3D chain, which is latency- and
+            # barrier-bound).  Modes 2 / 3 additionally build balanced sum trees, for float32 / float64
+            # operators: measured neutral (float32) and 1.2 % slower (float64 2-D chain), so not the default.
+            statements = [ex.Statement(st.target, ex.pair_odd_taps(st.value, mode in ("2", "3"))) for st in statements]
         ops.append(StencilOp(
             name=node.name, shape=shape, iterators=iterators, accesses=accesses,
             output_fields={node.name: [0] * len(shape)}, boundary_conditions=bcs,
