@@ -61,6 +61,9 @@ __device__ __forceinline__ void sf_mbar_expect_tx(void* bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sf_smem_addr(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void sf_mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sf_smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void sf_mbar_wait(void* bar, u32 parity) {
     u32 addr = sf_smem_addr(bar);
     u32 done = 0;
@@ -117,8 +120,12 @@ __device__ __forceinline__ void sf_tma_load_2d(void* dst, const CUtensorMap* map
 #ifdef SF_STORE_HINT
 #define SF_STG_V4F32 "st.global.L2::cache_hint.v4.f32 [%1], {%2, %3, %4, %5}, %6;"
 #define SF_STG_V2F64 "st.global.L2::cache_hint.v2.f64 [%1], {%2, %3}, %4;"
+#define SF_STG_V2F32 "st.global.L2::cache_hint.v2.f32 [%1], {%2, %3}, %4;"
 #define SF_STG_HINT_ARG , "l"(SF_STORE_HINT)
+#define SF_STG_HINT_ARG2 , "l"(SF_STORE_HINT)
 #else
+#define SF_STG_V2F32 "st.global.v2.f32 [%1], {%2, %3};"
+#define SF_STG_HINT_ARG2
 #define SF_STG_V4F32 "st.global.v4.f32 [%1], {%2, %3, %4, %5};"
 #define SF_STG_V2F64 "st.global.v2.f64 [%1], {%2, %3};"
 #define SF_STG_HINT_ARG
@@ -194,6 +201,16 @@ __device__ __forceinline__ float2 sf_fma2(float2 a, float2 b, float2 c) {
 }
 // results leave through explicit st.global (the output pointer is kept opaque to stop the compiler from
 // re-deriving it per row, which would otherwise demote these to generic stores)
+#ifdef SF_STG64
+template <int N>
+__device__ __forceinline__ void sf_stg_if(bool on, float* p, const float2 (&s)[N]) {
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+                     "@q " SF_STG_V2F32 "\n\t}"
+                     ::"r"((u32)on), "l"(p + 2 * q), "f"(s[q].x), "f"(s[q].y) SF_STG_HINT_ARG2 : "memory");
+}
+#else
 template <int N>
 __device__ __forceinline__ void sf_stg_if(bool on, float* p, const float2 (&s)[N]) {
 #pragma unroll
@@ -202,6 +219,7 @@ __device__ __forceinline__ void sf_stg_if(bool on, float* p, const float2 (&s)[N
                      "@q " SF_STG_V4F32 "\n\t}"
                      ::"r"((u32)on), "l"(p + 2 * q), "f"(s[q].x), "f"(s[q].y), "f"(s[q + 1].x), "f"(s[q + 1].y) SF_STG_HINT_ARG : "memory");
 }
+#endif
 template <int N>
 __device__ __forceinline__ void sf_stg_if(bool on, float* p, const float (&s)[N]) {
 #pragma unroll
@@ -234,10 +252,18 @@ __device__ __forceinline__ void sf_ldp(float2* dst, const float* __restrict__ p)
 }
 template <int V>
 __device__ __forceinline__ void sf_stp(float* __restrict__ p, const float2* src) {
+#ifdef SF_ST64
+    // one 64-bit store per packed pair: a 128-bit store wants its four registers in one aligned quad, and the
+    // pairs the packed arithmetic produces rarely sit in one (ptxas then copies them: 4 MOV per store)
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q)
+        asm volatile(SF_STS_V2F32 " [%0], {%1, %2};" ::"r"(sf_smem_addr(p + 2 * q)), "f"(src[q].x), "f"(src[q].y) : "memory");
+#else
     SfVec<float, V> t;
 #pragma unroll
     for (int q = 0; q < V / 2; ++q) { t.v[2 * q] = src[q].x; t.v[2 * q + 1] = src[q].y; }
     *reinterpret_cast<SfVec<float, V>*>(p) = t;
+#endif
 }
 """
 
@@ -251,10 +277,22 @@ def l2_hint_defines():
         text += "#define SF_LOAD_HINT 0x14F0000000000000ull\n"
     if bits & 2:
         text += "#define SF_STORE_HINT 0x12F0000000000000ull\n"
+    st64 = int(os.environ.get("SFB200_ST64", ST64_DEFAULT))
+    if st64 & 1:
+        # (ptxas fuses two plain 64-bit stores back into one 128-bit store; volatile ones stay apart)
+        text += "#define SF_ST64 1\n#define SF_STS_V2F32 \"{}\"\n".format(
+            "st.volatile.shared.v2.f32" if st64 & 4 else "st.shared.v2.f32")
+    if st64 & 2:
+        text += "#define SF_STG64 1\n"
     return text
 
 
 L2_HINT_DEFAULT = "3"
+ST64_DEFAULT = "0"
+SPLITBAR_DEFAULT = "0"
+SPLITLOOP_DEFAULT = "0"
+HALO_SKIP_DEFAULT = "0"
+SCHED_DEFAULT = "halving"
 
 
 class NotStreamable(Exception):
@@ -566,6 +604,9 @@ class Geometry:
         # warp (3-D, one column of warps) or one row of warps (2-D), and one named barrier per pair.
         nw = self.NT // 32
         self.NW = nw
+        # "flags" synchronisation: no CTA-wide barrier in the streamed loop; every published field has an
+        # mbarrier its producers arrive on and its consumers wait for a step later (StreamKernelGen.flags)
+        self.flags = (sync == "flags")
         self.pair = False
         if sync == "pair" and 2 <= nw <= 16:
             if ana.ndim == 3 and WC == 1 and 32 % KS == 0 and self.TC <= 256:
@@ -601,6 +642,10 @@ class Geometry:
         off += 8 * self.D * (self.NW if self.pair else 1)
         self.item_off = off            # persistent CTAs: the work item thread 0 fetched for everybody
         off += 16
+        self.sbar_off = off            # split CTA barrier (see StreamKernelGen.split_barrier)
+        off += 16
+        self.fbar_off = off            # one mbarrier per published field ("flags" synchronisation)
+        off += (8 * len(ana.fields) + 15) & ~15
         return off
 
 
@@ -647,8 +692,29 @@ class StreamKernelGen:
         self.U = self._choose_unroll(max(1, max_unroll))
         self.pipeline = os.environ.get("SFB200_PIPELINE", "1") != "0"
         self.fast_path = os.environ.get("SFB200_FASTPATH", "1") != "0"
+        self.split_loop = os.environ.get("SFB200_SPLITLOOP", SPLITLOOP_DEFAULT) != "0"
         self.with_bc = True
         self._tmp = 0
+        # split CTA barrier: instead of one __syncthreads at the end of a streamed step every warp *arrives*
+        # (one elected lane, after a __syncwarp) on an mbarrier as soon as it has published its last edge rows
+        # and read its last neighbour rows of the step, and *waits* at the end of the step -- what lies in
+        # between (the arithmetic and the stores of the group's last operator, which nobody in the CTA reads)
+        # overlaps with the slower warps catching up
+        self.split_barrier = (os.environ.get("SFB200_SPLITBAR", SPLITBAR_DEFAULT) != "0") and not geo.pair
+        # "flags" synchronisation (Geometry.flags): the CTA-wide barrier at the end of every streamed step is
+        # replaced by one mbarrier per published field.  A warp arrives on it right after it has stored its
+        # edge rows / columns of the field's new plane and waits for it a step later, just before it reads its
+        # neighbours' -- so warps may run up to a step apart, and the shared-memory, shuffle and arithmetic
+        # phases of different warps overlap instead of all warps hitting the same pipe at the same time (the
+        # FPGA design's processing elements are coupled the same way: through their FIFOs, not by a global
+        # clock-enable).  Needs every exchange ring to be read, in program order, before it is written again
+        # (see _flags_ok); anything else keeps the barrier.
+        self.fbar = {}
+        self.flags = bool(geo.flags and not geo.pair and self.pipeline and self.U % 2 == 0 and self._flags_ok())
+        if self.flags:
+            self.split_barrier = False
+        self._waited = set()
+        self.rotate_rows, self.skip_warps, self.skip_from = self._halo_warps()
         # how produced planes get their out-of-domain cells set to the boundary value (see _finish_field)
         self.bc_mode = os.environ.get("SFB200_BC_MODE", "auto")
         # persistent scheduling (see schedule_work): tiles of the in-plane grid
@@ -667,6 +733,48 @@ class StreamKernelGen:
             # long-running tiles do not have to spare (hdiff: 123 -> 128 registers and a spill, 0.163 -> 0.180 ms)
             self.bc_mode = "thread" if self.persistent else "cta"
 
+    def _published(self, info):
+        return bool((info.row_ring and info.name not in self.geo.direct) or info.col_ring)
+
+    def _flags_ok(self):
+        """Flag synchronisation is safe when, for every published field, (1) its ring is two deep and read at
+        age 1 only, (2) its only reader through the ring is the operator right after its producer, whose
+        neighbour data is gathered *before* the producer's new plane is published (software pipelining), so
+        that a warp's arrival for step t also says "my reads of step t-1's slot are done"; (3) every streamed
+        input is published (its arrival doubles as "tile slot read" for the TMA ring)."""
+        a = self.ana
+        names = [op.name for op in self.ops]
+        for info in a.fields.values():
+            if info.kind == "ext" and not self._published(info):
+                return False
+            if not self._published(info):
+                continue
+            if info.row_ring not in (0, 2) or info.col_ring not in (0, 2):
+                return False
+            readers = []
+            for op in self.ops:
+                for (field, d, dj, dk) in a.taps[op.name]:
+                    if field == info.name and a._is_exchange(dj, dk) and op.name not in readers:
+                        readers.append(op.name)
+            expect = 0 if info.kind == "ext" else names.index(info.name) + 1
+            if expect >= len(names) or readers != [names[expect]]:
+                return False
+            if not self._can_gather_early(self.ops[expect]):
+                return False
+            self.fbar[info.name] = len(self.fbar)
+        return bool(self.fbar)
+
+    def _flag_wait(self, info, age, u, indent=2):
+        """Before the first read of what other warps published of ``info`` at step (t - age)."""
+        if not self.flags or info.name not in self.fbar or (info.name, age) in self._waited:
+            return
+        self._waited.add((info.name, age))
+        self.emit("sf_mbar_wait(&fbars[{}], {}u);".format(self.fbar[info.name], (u - age) % 2), indent)
+
+    def _flag_arrive(self, info):
+        if self.flags and info.name in self.fbar:
+            self.emit("__syncwarp(); if (sf_elect_one()) sf_mbar_arrive(&fbars[{}]);".format(self.fbar[info.name]), 2)
+
     # ------------------------------------------------------------------ unrolling
     def _choose_unroll(self, cap):
         a, g = self.ana, self.geo
@@ -679,6 +787,7 @@ class StreamKernelGen:
             for n in periods:
                 base = base * n // math.gcd(base, n)
             u = base * -(-wmax // base)          # smallest multiple of the smem periods covering every window
+            u *= max(1, int(os.environ.get("SFB200_UNROLL_MULT", "1")))   # (experiment: amortise the trip-end copies)
             if u <= cap:
                 return u
         return 1
@@ -775,7 +884,10 @@ class StreamKernelGen:
         else:
             e("const int lane = threadIdx.x % {};          // column slot within the row".format(g.KS))
             e("const int warp = threadIdx.x / {};          // row group".format(g.KS))
-        e("const int wr = warp / {};".format(g.WC))
+        if self.rotate_rows:
+            e("const int wr = (warp + {}) % {};        // row groups dealt to the warps rotated by one (see _halo_warps)".format(g.WR - 1, g.WR))
+        else:
+            e("const int wr = warp / {};".format(g.WC))
         e("const int wc = warp % {};".format(g.WC))
         e("(void)wr; (void)wc;")
         e("const int c0 = (wc * {} + lane) * {};            // first owned column inside the tile".format(g.KS, V))
@@ -794,6 +906,10 @@ class StreamKernelGen:
         e("unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.bar_off))
         e("if (threadIdx.x == 0) {")
         e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D * (g.NW if g.pair else 1)), 2)
+        if self.split_barrier:
+            e("sf_mbar_init(sf_smem + {}, {});".format(g.sbar_off, g.NT // 32), 2)
+        for n in range(len(self.fbar) if self.flags else 0):
+            e("sf_mbar_init(sf_smem + {}, {});".format(g.fbar_off + 8 * n, g.NT // 32), 2)
         e("sf_fence_barrier_init();", 2)
         e("}")
         e("__syncthreads();")
@@ -817,6 +933,14 @@ class StreamKernelGen:
         else:
             e("int slot = 0; u32 phase = 0;")
         e("const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform")
+        if self.skip_from < len(self.ops):
+            e("const bool halo_warp = {};".format(" || ".join("warp_u == {}".format(w) for w in self.skip_warps)))
+        if self.flags:
+            e("unsigned long long* const fbars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.fbar_off))
+        if self.split_barrier:
+            e("unsigned long long* const sbar = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.sbar_off))
+            if U % 2:
+                e("u32 sphase = 0;")
 
         # ---- the segment(s) this CTA streams: a tile and a range of planes of the streamed dimension
         gx = -(-self.NK // g.BK)
@@ -945,31 +1069,60 @@ class StreamKernelGen:
             e("for (int p = 0; p < {P}; ++p) if (t_begin + p < t_end) issue(t_begin + p, (slot + p) % {D});".format(
                 P=g.P, D=g.D), 2)
         e("}")
-        e("#pragma unroll 1")
-        e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
         needs_bc = [i for i in a.fields.values() if self._needs_fixup(i)]
         # ``copy`` boundaries are resolved by the consuming operator: its trips near the border need the code too
         needs_bc += [a.fields[op] for (op, _) in sorted(a.copy_taps) if a.fields[op] not in needs_bc]
         needs_bc += [a.fields[f] for (_, f) in sorted(a.copy_taps) if a.fields[f] not in needs_bc]
-        variants = [True]
-        if needs_bc and self.fast_path:
-            # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no
-            # boundary values: it runs a copy of the steps without any of that code
+        flip = static_d and (U // g.D) % 2 == 1
+        if needs_bc and self.fast_path and self.split_loop:
+            # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no boundary
+            # values: it runs a copy of the steps without any of that code.  The two copies are separate
+            # loops -- runs of fast trips, single trips with the boundary code in between -- rather than the
+            # two arms of a branch inside one loop: the register assignment of the fast loop is then its own
+            # (no copies at the join of the arms: 57 MOV per trip of the Jacobi-3D pass)
             lag_max = max(i.lag for i in needs_bc)
             lag_min = min(i.lag for i in needs_bc)
-            e("const bool fast = __all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}));".format(
-                lag_max, U - 1, lag_min, self.NS), 2)
-            variants = [False, True]
-        for with_bc in variants:
-            self.with_bc = with_bc
-            if len(variants) == 2:
-                e("if (fast) {" if not with_bc else "} else {", 2)
+            cond = "__all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}))".format(
+                lag_max, U - 1, lag_min, self.NS)
+            e("int t0 = t_begin;")
+            e("#pragma unroll 1")
+            e("while (t0 < t_end) {")
+            e("#pragma unroll 1", 2)
+            e("while (t0 < t_end && {}) {{".format(cond), 2)
+            self.with_bc = False
             self._emit_steps(ext, static_d)
-        if len(variants) == 2:
+            if flip:
+                e("phase ^= 1u;", 2)
+            e("t0 += {};".format(U), 2)
             e("}", 2)
-        if static_d and (U // g.D) % 2 == 1:
-            e("phase ^= 1u;", 2)
-        e("}")
+            e("if (t0 < t_end) {", 2)
+            self.with_bc = True
+            self._emit_steps(ext, static_d)
+            if flip:
+                e("phase ^= 1u;", 2)
+            e("t0 += {};".format(U), 2)
+            e("}", 2)
+            e("}")
+        else:
+            e("#pragma unroll 1")
+            e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
+            variants = [True]
+            if needs_bc and self.fast_path:
+                lag_max = max(i.lag for i in needs_bc)
+                lag_min = min(i.lag for i in needs_bc)
+                e("const bool fast = __all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}));".format(
+                    lag_max, U - 1, lag_min, self.NS), 2)
+                variants = [False, True]
+            for with_bc in variants:
+                self.with_bc = with_bc
+                if len(variants) == 2:
+                    e("if (fast) {" if not with_bc else "} else {", 2)
+                self._emit_steps(ext, static_d)
+            if len(variants) == 2:
+                e("}", 2)
+            if flip:
+                e("phase ^= 1u;", 2)
+            e("}")
         if self.peer_push:
             # slab mode: the planes of this segment that a neighbouring GPU reads as halo follow the
             # segment out (all result stores of the CTA are visible to it after the barrier)
@@ -1030,24 +1183,25 @@ class StreamKernelGen:
                 self.slot_expr = "slot"
                 nxt = "(slot + {P}) % {D}".format(P=g.P, D=g.D)
                 ph = "phase"
+            self._waited = set()
+            if self.flags:
+                # every warp has read its rows of the plane in the TMA slot about to be refilled once it has
+                # published them: the arrivals of the previous step on the streamed inputs' barriers
+                for i in ext:
+                    self._flag_wait(i, 1, u)
             e("if (issuer && t + {P} < t_end) {{ if (sf_elect_one()) issue(t + {P}, {nxt}); }}".format(P=g.P, nxt=nxt), 2)
-            gathered = {}
-            if self.pipeline and self._can_gather_early(self.ops[0]):
-                # neighbour data of the first operator is a step old: fetch it while the TMA lands
-                gathered[0] = self._gather_op(self.ops[0], u, 0)
-            e("sf_mbar_wait(&wbars[{}], {});".format(self.slot_expr, ph), 2)
-            for i in ext:
-                self._produce_ext(i, u)
-            for k, op in enumerate(self.ops):
-                if k not in gathered:
-                    gathered[k] = self._gather_op(op, u, k)
-                if self.pipeline and k + 1 < len(self.ops) and self._can_gather_early(self.ops[k + 1]):
-                    # software pipelining: the shuffles / ring loads of the next operator are issued
-                    # before this operator's arithmetic, which hides their latency
-                    gathered[k + 1] = self._gather_op(self.ops[k + 1], u, k + 1)
-                self._produce_op(op, u, gathered.pop(k))
+            last_comm = self._emit_ops(u, ext, ph, len(self.ops))
             if g.pair:
                 e("sf_sync_neighbours<{}>(warp_u);".format(g.NW), 2)
+            elif self.flags:
+                pass
+            elif self.split_barrier:
+                self.lines.insert(last_comm, "  " * 2 + "__syncwarp(); if (sf_elect_one()) sf_mbar_arrive(sbar);")
+                # (segments are whole trips of U steps: with an even U the phase of a step is static)
+                if U % 2:
+                    e("sf_mbar_wait(sbar, sphase); sphase ^= 1u;", 2)
+                else:
+                    e("sf_mbar_wait(sbar, {}u);".format(u % 2), 2)
             else:
                 e("__syncthreads();", 2)
             if not static_d:
@@ -1058,6 +1212,75 @@ class StreamKernelGen:
                 if i.col_ring and not self.static(i.col_ring):
                     e("if (++xc_{f} == {n}) xc_{f} = 0;".format(f=self.fid[i.name], n=i.col_ring), 2)
             e("}", 2)
+
+    def _emit_ops(self, u, ext, ph, n_ops):
+        """One streamed step of a thread: the new plane of every input, then the first ``n_ops`` operators.
+        Returns the position (in ``self.lines``) after the last shared-memory read / write of the step."""
+        g, a, e = self.geo, self.ana, self.emit
+        ops = self.ops[:n_ops]
+        gathered = {}
+        if ops and self.pipeline and self._can_gather_early(ops[0]):
+            # neighbour data of the first operator is a step old: fetch it while the TMA lands
+            gathered[0] = self._gather_op(ops[0], u, 0)
+        e("sf_mbar_wait(&wbars[{}], {});".format(self.slot_expr, ph), 2)
+        for i in ext:
+            self._produce_ext(i, u)
+        last_comm = len(self.lines)
+        for k, op in enumerate(ops):
+            if k == self.skip_from:
+                # warps that hold nothing but outer halo rows (see _halo_warps) leave the step here
+                e("if (!halo_warp) {", 2)
+            if k not in gathered:
+                gathered[k] = self._gather_op(op, u, k)
+                last_comm = len(self.lines)
+            if self.pipeline and k + 1 < len(ops) and self._can_gather_early(ops[k + 1]):
+                # software pipelining: the shuffles / ring loads of the next operator are issued
+                # before this operator's arithmetic, which hides their latency
+                gathered[k + 1] = self._gather_op(ops[k + 1], u, k + 1)
+                last_comm = len(self.lines)
+            self._produce_op(op, u, gathered.pop(k))
+            info = a.fields[op.name]
+            if info.consumed and (info.row_ring or info.col_ring):
+                last_comm = len(self.lines)
+        if self.skip_from < len(ops):
+            e("}", 2)
+        return last_comm
+
+    def _halo_warps(self):
+        """3-D tiles: (rotate, warps, first skipped operator).  The outermost halo rows of a tile only feed the
+        first operators of the group -- with a halo of 4 rows and 3 rows per thread, rows 0-2 and TR-3..TR-1 are
+        read by the first two of four chained operators and by nothing after.  When the row groups are dealt
+        to the warps *rotated by one* (two groups per warp at 16 threads per row: warp 0 then holds the last and
+        the first group, i.e. only such rows), that warp can leave a step early: it skips the remaining
+        operators, whose results on its rows nobody stores or reads for a stored cell (1/24 of the arithmetic
+        and exchange traffic of the Jacobi-3D pass).  With a warp per row group the first and the last warp
+        qualify without rotation."""
+        g, a = self.geo, self.ana
+        none = (False, [], len(self.ops))
+        if a.ndim != 3 or g.WC != 1 or g.pair or os.environ.get("SFB200_HALO_SKIP", HALO_SKIP_DEFAULT) == "0":
+            return none
+        if self.flags or self.split_barrier or g.NT % 32 or 32 % g.KS:
+            return none
+        gpw = 32 // g.KS
+        best = none
+        for rot in ((False, True) if gpw > 1 else (False,)):
+            per_warp = {}
+            for hw in range(g.NT // 32):
+                groups = [((hw * gpw + h) + (g.WR - 1 if rot else 0)) % g.WR for h in range(gpw)]
+                first_unneeded = len(self.ops)
+                for k in range(len(self.ops) - 1, -1, -1):
+                    info = a.fields[self.ops[k].name]
+                    lo, hi = g.HJ0 - info.need[0], g.TR - g.HJ1 + info.need[1]
+                    if any(lo <= wr * g.R + r < hi for wr in groups for r in range(g.R)):
+                        break
+                    first_unneeded = k
+                per_warp[hw] = first_unneeded
+            cut = min(per_warp.values())
+            warps = [hw for hw, k in per_warp.items() if k == cut]
+            if cut < len(self.ops) and (best[2] == len(self.ops) or
+                                         (len(self.ops) - cut) * len(warps) > (len(self.ops) - best[2]) * len(best[1])):
+                best = (rot, warps, cut)
+        return best
 
     def _box(self):
         return list(self.geo.box)
@@ -1146,6 +1369,8 @@ class StreamKernelGen:
                 for q in range(n):
                     e("sf_sts_if(lane == 31 && wc < {last}, {{base}} + {{o}}, {{c}});".format(last=g.WC - 1).format(
                         base=base, o=(R + r) * n + q, c=self.cellref("nv[{}]".format(r), V - n + q)), 2)
+        if self._published(info):
+            self._flag_arrive(info)
 
     # ------------------------------------------------------------------ lower-dimensional inputs
     def _aux_bc(self, field):
@@ -1266,6 +1491,8 @@ class StreamKernelGen:
             src = a.fields[field]
             f = self.fid[field]
             tag = "o{}_{}_{}_{}".format(k, f, age, _fmt_off(rr))
+            if not (0 <= rr < R) or (src.col_ring and (nl or nr)):
+                self._flag_wait(src, age, u, 3)
             if 0 <= rr < R:
                 vec = "w_{}[{}][{}]".format(f, self.wslot(src, age, u), rr)
                 names[(field, age, rr)] = (vec, tag)
@@ -1902,7 +2129,7 @@ def choose_chunk(n_stream, tiles, overhead, sms=148):
     return best[1]
 
 
-def schedule_work(n_tiles, n_planes, slots, overhead):
+def schedule_work(n_tiles, n_planes, slots, overhead, edge_tiles=None):
     """Work items of a streamed pass for its persistent CTAs: ``[(tile, p_begin, p_end), ...]``, planes
     relative to the first plane of the slab, in the order the CTAs fetch them (CTA b starts with item
     b, every CTA then takes the next unclaimed one).
@@ -1921,6 +2148,9 @@ def schedule_work(n_tiles, n_planes, slots, overhead):
       self-scheduling): each round hands about half of what is left to ``slots`` items of equal length,
       tile-minor so that the CTAs of a round hold adjacent tiles of one range; the last items are short
       (a few times the warm-up), which bounds how far apart the CTAs finish."""
+    mode = os.environ.get("SFB200_SCHED", SCHED_DEFAULT)
+    if mode == "lpt" and edge_tiles is not None and n_tiles >= 2 * slots:
+        return _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles)
     whole = int((n_tiles / float(slots)) / (1.0 + EDGE_SLOWDOWN)) * slots
     items = [(t, 0, n_planes) for t in range(whole)]
     tiles = n_tiles - whole
@@ -1951,6 +2181,38 @@ def schedule_work(n_tiles, n_planes, slots, overhead):
     nchunk = -(-n_planes // ci)
     if -(-n_tiles * nchunk // slots) * (ci + overhead) < cost:
         return [(t, c * ci, min(n_planes, (c + 1) * ci)) for c in range(nchunk) for t in range(n_tiles)]
+    return items
+
+
+def _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles):
+    """Alternative list for passes with at least two tiles per slot: every full wave of tiles streams whole
+    (one warm-up per tile), the *domain-edge tiles first* -- they are the slow ones, and the CTAs that drew
+    them simply fetch their next tile later (longest-processing-time-first) -- and only the tiles that do not
+    fill a wave are cut into halving plane ranges that even out the finish."""
+    edge = [t for t in range(n_tiles) if t in edge_tiles]
+    inner = [t for t in range(n_tiles) if t not in edge_tiles]
+    order = edge + inner
+    whole = (n_tiles // slots) * slots
+    items = [(t, 0, n_planes) for t in order[:whole]]
+    rest = order[whole:]
+    if rest:
+        pieces = max(1, slots // len(rest))
+        floor_ = max(2 * overhead, 16)
+        pos, share = 0, 0.75
+        while pos < n_planes:
+            left = n_planes - pos
+            size = max(floor_, -(-int(left * share) // pieces))
+            share = 0.5
+            if left - pieces * size < floor_:
+                k = max(1, min(pieces, left // floor_))
+                size = -(-left // k)
+            else:
+                k = pieces
+            for c in range(k):
+                b, e_ = pos + c * size, min(n_planes, pos + (c + 1) * size)
+                if b < e_:
+                    items.extend((t, b, e_) for t in rest)
+            pos += k * size
     return items
 
 
@@ -2000,7 +2262,18 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
         offers (``resident_ctas`` = occupancy of the loaded function x SMs, supplied by the executor;
         the estimate otherwise)."""
         slots = resident_ctas or SM_COUNT * resident
-        return schedule_work(gx * gy, max(1, e_ - b), slots, overhead)
+        # tiles with cells outside the domain run the boundary code in every step
+        edge = set()
+        for t in range(gx * gy):
+            kx, jy = t % gx, t // gx
+            k0 = kx * geo.BK - geo.HK0
+            if k0 < 0 or k0 + geo.TC > NK:
+                edge.add(t)
+            if ana.ndim == 3:
+                j0 = jy * geo.BJ - geo.HJ0
+                if j0 < 0 or j0 + geo.TR > NJ:
+                    edge.add(t)
+        return schedule_work(gx * gy, max(1, e_ - b), slots, overhead, edge_tiles=edge)
 
     def work_table(b, e_, resident_ctas=None):
         return pack_work_table(work_items(b, e_, resident_ctas))
@@ -2023,7 +2296,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
                               "prefetch": geo.P, "persistent": gen.persistent, "peer_push": gen.peer_push,
-                              "tiles": gx * gy, "sync": "pair" if geo.pair else "cta", "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "tiles": gx * gy, "sync": "pair" if geo.pair else ("flags" if gen.flags else "cta"), "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "halo_skip": [gen.rotate_rows, gen.skip_warps, gen.skip_from], "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "register_estimate": ana.register_estimate(geo.R, geo.V),
