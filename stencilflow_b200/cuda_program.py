@@ -536,8 +536,8 @@ class CudaProgram:
         span0 = min(need[a][0] for a in inputs)
         span1 = max(need[a][1] for a in inputs)
         schedule = []
-        for s in range(pieces):
-            e_in = span0 + ((span1 - span0) * (s + 1)) // pieces
+        max_reach = max([1] + [max(r) for rr in reach for r in rr.values()])
+        for s, e_in in enumerate(self._piece_ends(span0, span1, pieces, max_reach)):
             step = {"h2d": [], "launch": [], "d2h": [], "h2d_whole": whole if s == 0 else []}
             for a in inputs:
                 e_a = min(max(e_in, avail[a]), need[a][1])
@@ -565,6 +565,33 @@ class CudaProgram:
             schedule.append(step)
         assert all(d == t[1] for d, t in zip(done, target)) and all(v == own1 for v in out_done.values())
         return schedule
+
+    @staticmethod
+    def _piece_ends(span0, span1, pieces, max_reach):
+        """End planes of the pieces of a pipelined call.  The call costs the longer copy direction plus what
+        cannot overlap: the upload of the first piece and the download of the last.  So the pieces at both
+        ends are short -- 4 x the largest reach, doubling towards the uniform size in the middle -- and only the
+        middle of the domain is cut evenly (``SFB200_PIPELINE_RAMP=0``: all pieces equal)."""
+        n = span1 - span0
+        uniform = [span0 + (n * (s + 1)) // pieces for s in range(pieces)]
+        if os.environ.get("SFB200_PIPELINE_RAMP", "1") == "0":
+            return uniform
+        base = n // pieces
+        head, size = [], max(4 * max_reach, 8)
+        while size < base:
+            head.append(size)
+            size *= 2
+        if not head or 2 * sum(head) + base > n:
+            return uniform
+        middle = n - 2 * sum(head)
+        k = max(1, int(round(middle / float(base))))
+        sizes = head + [middle // k + (1 if q < middle % k else 0) for q in range(k)] + head[::-1]
+        ends, pos = [], span0
+        for sz in sizes:
+            pos += sz
+            ends.append(pos)
+        assert ends[-1] == span1
+        return ends
 
     # ------------------------------------------------------------------ caller-owned host arrays
     REGISTER_MIN_BYTES = 32 << 20
@@ -621,10 +648,12 @@ class CudaProgram:
                 self._build_packs()
             self._pipe = self._pipeline_schedule(pieces)
             self._pipe_key = key
-            if self._pipe is not None and not hasattr(self, "_pipe_streams"):
-                self._pipe_streams = (self.rt.stream_create(), self.rt.stream_create())
-                self._pipe_events = [(self.rt.event_create(False), self.rt.event_create(False))
-                                     for _ in range(pieces)]
+            if self._pipe is not None:
+                if not hasattr(self, "_pipe_streams"):
+                    self._pipe_streams = (self.rt.stream_create(), self.rt.stream_create())
+                    self._pipe_events = []
+                while len(self._pipe_events) < len(self._pipe):      # one pair per piece (pieces may be ramped)
+                    self._pipe_events.append((self.rt.event_create(False), self.rt.event_create(False)))
         if self._pipe is None:
             return False
         rtm, fields = self.rt, self.program.fields

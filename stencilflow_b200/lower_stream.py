@@ -290,9 +290,9 @@ def l2_hint_defines():
 L2_HINT_DEFAULT = "3"
 ST64_DEFAULT = "0"
 SPLITBAR_DEFAULT = "0"
-SPLITLOOP_DEFAULT = "0"
+SPLITLOOP_DEFAULT = "auto"
 HALO_SKIP_DEFAULT = "0"
-SCHED_DEFAULT = "halving"
+SCHED_DEFAULT = "lpt"
 
 
 class NotStreamable(Exception):
@@ -692,7 +692,10 @@ class StreamKernelGen:
         self.U = self._choose_unroll(max(1, max_unroll))
         self.pipeline = os.environ.get("SFB200_PIPELINE", "1") != "0"
         self.fast_path = os.environ.get("SFB200_FASTPATH", "1") != "0"
-        self.split_loop = os.environ.get("SFB200_SPLITLOOP", SPLITLOOP_DEFAULT) != "0"
+        # separate loops for the trips with and without boundary code (see generate): measured +1.4 % on the
+        # float64 2-D chain; the 3-D Jacobi pass sits at its register limit and spills with it (-19 %)
+        split = os.environ.get("SFB200_SPLITLOOP", SPLITLOOP_DEFAULT)
+        self.split_loop = (ana.ndim == 2) if split == "auto" else split != "0"
         self.with_bc = True
         self._tmp = 0
         # split CTA barrier: instead of one __syncthreads at the end of a streamed step every warp *arrives*
@@ -715,6 +718,7 @@ class StreamKernelGen:
             self.split_barrier = False
         self._waited = set()
         self.rotate_rows, self.skip_warps, self.skip_from = self._halo_warps()
+        self.ops_limit = len(ops)
         # how produced planes get their out-of-domain cells set to the boundary value (see _finish_field)
         self.bc_mode = os.environ.get("SFB200_BC_MODE", "auto")
         # persistent scheduling (see schedule_work): tiles of the in-plane grid
@@ -1073,56 +1077,70 @@ class StreamKernelGen:
         # ``copy`` boundaries are resolved by the consuming operator: its trips near the border need the code too
         needs_bc += [a.fields[op] for (op, _) in sorted(a.copy_taps) if a.fields[op] not in needs_bc]
         needs_bc += [a.fields[f] for (_, f) in sorted(a.copy_taps) if a.fields[f] not in needs_bc]
-        flip = static_d and (U // g.D) % 2 == 1
-        if needs_bc and self.fast_path and self.split_loop:
-            # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no boundary
-            # values: it runs a copy of the steps without any of that code.  The two copies are separate
-            # loops -- runs of fast trips, single trips with the boundary code in between -- rather than the
-            # two arms of a branch inside one loop: the register assignment of the fast loop is then its own
-            # (no copies at the join of the arms: 57 MOV per trip of the Jacobi-3D pass)
-            lag_max = max(i.lag for i in needs_bc)
-            lag_min = min(i.lag for i in needs_bc)
-            cond = "__all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}))".format(
-                lag_max, U - 1, lag_min, self.NS)
-            e("int t0 = t_begin;")
-            e("#pragma unroll 1")
-            e("while (t0 < t_end) {")
-            e("#pragma unroll 1", 2)
-            e("while (t0 < t_end && {}) {{".format(cond), 2)
-            self.with_bc = False
-            self._emit_steps(ext, static_d)
-            if flip:
-                e("phase ^= 1u;", 2)
-            e("t0 += {};".format(U), 2)
-            e("}", 2)
-            e("if (t0 < t_end) {", 2)
-            self.with_bc = True
-            self._emit_steps(ext, static_d)
-            if flip:
-                e("phase ^= 1u;", 2)
-            e("t0 += {};".format(U), 2)
-            e("}", 2)
-            e("}")
-        else:
-            e("#pragma unroll 1")
-            e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
-            variants = [True]
-            if needs_bc and self.fast_path:
+        def emit_loop(n_ops):
+            self.ops_limit = n_ops
+            flip = static_d and (U // g.D) % 2 == 1
+            if needs_bc and self.fast_path and self.split_loop:
+                # a trip whose planes all lie inside the domain, in a CTA whose cells all do, needs no boundary
+                # values: it runs a copy of the steps without any of that code.  The two copies are separate
+                # loops -- runs of fast trips, single trips with the boundary code in between -- rather than the
+                # two arms of a branch inside one loop: the register assignment of the fast loop is then its own
+                # (no copies at the join of the arms: 57 MOV per trip of the Jacobi-3D pass)
                 lag_max = max(i.lag for i in needs_bc)
                 lag_min = min(i.lag for i in needs_bc)
-                e("const bool fast = __all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}));".format(
-                    lag_max, U - 1, lag_min, self.NS), 2)
-                variants = [False, True]
-            for with_bc in variants:
-                self.with_bc = with_bc
-                if len(variants) == 2:
-                    e("if (fast) {" if not with_bc else "} else {", 2)
+                cond = "__all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}))".format(
+                    lag_max, U - 1, lag_min, self.NS)
+                e("int t0 = t_begin;")
+                e("#pragma unroll 1")
+                e("while (t0 < t_end) {")
+                e("#pragma unroll 1", 2)
+                e("while (t0 < t_end && {}) {{".format(cond), 2)
+                self.with_bc = False
                 self._emit_steps(ext, static_d)
-            if len(variants) == 2:
+                if flip:
+                    e("phase ^= 1u;", 2)
+                e("t0 += {};".format(U), 2)
                 e("}", 2)
-            if flip:
-                e("phase ^= 1u;", 2)
+                e("if (t0 < t_end) {", 2)
+                self.with_bc = True
+                self._emit_steps(ext, static_d)
+                if flip:
+                    e("phase ^= 1u;", 2)
+                e("t0 += {};".format(U), 2)
+                e("}", 2)
+                e("}")
+            else:
+                e("#pragma unroll 1")
+                e("for (int t0 = t_begin; t0 < t_end; t0 += {}) {{".format(U))
+                variants = [True]
+                if needs_bc and self.fast_path:
+                    lag_max = max(i.lag for i in needs_bc)
+                    lag_min = min(i.lag for i in needs_bc)
+                    e("const bool fast = __all_sync(0xffffffffu, interior && (t0 - ({}) >= 0) && (t0 + {} - ({}) < {}));".format(
+                        lag_max, U - 1, lag_min, self.NS), 2)
+                    variants = [False, True]
+                for with_bc in variants:
+                    self.with_bc = with_bc
+                    if len(variants) == 2:
+                        e("if (fast) {" if not with_bc else "} else {", 2)
+                    self._emit_steps(ext, static_d)
+                if len(variants) == 2:
+                    e("}", 2)
+                if flip:
+                    e("phase ^= 1u;", 2)
+                e("}")
+
+        if self.skip_from < len(self.ops):
+            # the warps that hold nothing but outer halo rows (see _halo_warps) stream through their own copy
+            # of the loop, which runs the leading operators only; barriers are counted, not matched by
+            # address, so the two loops meet at every step all the same
+            e("if (halo_warp) {")
+            emit_loop(self.skip_from)
+            e("} else {")
+            emit_loop(len(self.ops))
             e("}")
+        else:
+            emit_loop(len(self.ops))
         if self.peer_push:
             # slab mode: the planes of this segment that a neighbouring GPU reads as halo follow the
             # segment out (all result stores of the CTA are visible to it after the barrier)
@@ -1190,7 +1208,7 @@ class StreamKernelGen:
                 for i in ext:
                     self._flag_wait(i, 1, u)
             e("if (issuer && t + {P} < t_end) {{ if (sf_elect_one()) issue(t + {P}, {nxt}); }}".format(P=g.P, nxt=nxt), 2)
-            last_comm = self._emit_ops(u, ext, ph, len(self.ops))
+            last_comm = self._emit_ops(u, ext, ph, self.ops_limit)
             if g.pair:
                 e("sf_sync_neighbours<{}>(warp_u);".format(g.NW), 2)
             elif self.flags:
@@ -1227,9 +1245,6 @@ class StreamKernelGen:
             self._produce_ext(i, u)
         last_comm = len(self.lines)
         for k, op in enumerate(ops):
-            if k == self.skip_from:
-                # warps that hold nothing but outer halo rows (see _halo_warps) leave the step here
-                e("if (!halo_warp) {", 2)
             if k not in gathered:
                 gathered[k] = self._gather_op(op, u, k)
                 last_comm = len(self.lines)
@@ -1242,8 +1257,6 @@ class StreamKernelGen:
             info = a.fields[op.name]
             if info.consumed and (info.row_ring or info.col_ring):
                 last_comm = len(self.lines)
-        if self.skip_from < len(ops):
-            e("}", 2)
         return last_comm
 
     def _halo_warps(self):

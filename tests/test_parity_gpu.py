@@ -347,6 +347,42 @@ def test_pipelined_host_call(gpu, kind, monkeypatch):
         assert err <= TOL[ref.dtype.name]
 
 
+@pytest.mark.parametrize("kind", ["jacobi3d_64ops", "jacobi2d_16ops_f64"])
+def test_long_chains_match_oracle(gpu, kind):
+    """The shapes of BASELINE configs 4 and 3 at sizes the oracle finishes in seconds: a 64-operator
+    Jacobi-3D chain (16 passes of 4 operators with the plan of the benchmark, intermediates sharing two
+    ping-pong buffers; float32 drift over 64 stages stays inside the tolerance) and the 16-operator float64
+    2-D ``shrink`` chain on its tuned plan (2-warp CTAs, 8 operators per pass)."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200 import programs, synthetic
+    from stencilflow_b200.cuda_program import CudaProgram
+    from stencilflow_b200.planner import PlanOptions
+    if kind == "jacobi3d_64ops":
+        shape, halo = (112, 96, 128), 0
+        prog = programs.jacobi3d_chain(list(shape), 64)
+        inputs = {"a": synthetic.fill_hash(shape, np.float32, 4321)}
+        opts = PlanOptions(max_depth=4, rows_per_thread=3, warps=12, prefetch=5)
+        out = "b63"
+    else:
+        shape, halo = (4096, 8192), 16
+        prog = programs.jacobi2d_chain(list(shape), 16)
+        inputs = {"a": synthetic.fill_hash(shape, np.float64, 77)}
+        opts = PlanOptions(max_depth=8, vector=4, warps=2, prefetch=5)
+        out = "b15"
+    path = programs.write_program(prog, "longchain_" + kind)
+    p = CudaProgram(path, plan_options=opts)
+    streamed = [l for l in p.lowered.launches if l.family == "streamed"]
+    assert len(streamed) == (16 if kind == "jacobi3d_64ops" else 2)
+    if kind == "jacobi3d_64ops":
+        assert len(set(p.plan.buffer_assignment().values())) <= 4          # input, output, two ping-pong buffers
+    got = np.zeros(shape, dtype=inputs["a"].dtype)
+    p(a_host=inputs["a"], **{out + "_host": got})
+    p.close()
+    expected = rn.run_reference(path, inputs)[out]
+    err = rn.max_relative_error(rn.trim_halo(expected, halo), rn.trim_halo(got, halo))
+    assert err <= TOL[expected.dtype.name], err
+
+
 PAIR_VARIANTS_3D = [
     # (max_depth, rows_per_thread, warps, threads per row, prefetch): neighbour-only synchronisation with
     # per-warp TMA staging, and deeper TMA rings under both synchronisation schemes

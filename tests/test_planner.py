@@ -26,11 +26,37 @@ def test_config1_plan(native_lib):
     info = launches[0].info
     assert info["tile"] == [72, 64] and info["R"] == 3 and info["prefetch"] == 5 and info["unroll"] == 6
     assert launches[0].block == (384, 1, 1) and launches[0].smem <= 227 * 1024
-    # persistent CTAs, one per SM, fetching items from a shared list: one wave of whole tiles (neighbours in
-    # lockstep), then the other 156 tiles in rounds of plane ranges that halve -- 512, 256, ... 32 -- so that
-    # the CTAs finish together although domain-edge tiles are slower
+    # persistent CTAs, one per SM, fetching items from a shared list: two waves of whole tiles, the 66
+    # domain-edge tiles (slower: boundary code in every step) first, then the 8 tiles that do not fill a wave
+    # in halving plane ranges so that the CTAs finish together
     assert info["persistent"] and info["tiles"] == 19 * 16
     assert launches[0].grid_fn(0, 1024) == (148, 1, 1)
+    items = info["work_items_fn"](0, 1024)
+    whole = items[:296]
+    assert all((p0, p1) == (0, 1024) for _, p0, p1 in whole) and len({t for t, _, _ in whole}) == 296
+    edge = {t for t in range(304) if t % 19 in (0, 18) or t // 19 in (0, 15)}
+    assert {t for t, _, _ in whole[:len(edge)]} == edge
+    rest = items[296:]
+    assert len({t for t, _, _ in rest}) == 8 and not ({t for t, _, _ in rest} & {t for t, _, _ in whole})
+    lengths = [p1 - p0 for _, p0, p1 in rest]
+    assert lengths == sorted(lengths, reverse=True) and lengths[-1] <= 32
+    for t in {t for t, _, _ in rest}:
+        covered = sorted((p0, p1) for tt, p0, p1 in rest if tt == t)
+        assert covered[0][0] == 0 and covered[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    steps = sum(p1 - p0 + info["stream_overhead_planes"] for _, p0, p1 in items) / 148.0
+    assert steps <= 1.02 * (19 * 16 * 1024 / 148.0)
+    table = info["work_fn"](0, 1024)
+    assert table[:3] == [0, 0, len(items)] and table[3:9] == [items[0][0], 0, 1024, items[1][0], 0, 1024]
+    # algorithmic bytes of a pass: the field in, the field out
+    assert launches[0].reads == ["a"] and launches[0].writes == ["b3"]
+
+
+def test_config1_halving_list(native_lib, monkeypatch):
+    """SFB200_SCHED=halving: the list the longest-first one replaced -- one wave of whole tiles (neighbours in
+    lockstep), then the other 156 tiles in rounds of plane ranges that halve, 512, 256, ... 32."""
+    monkeypatch.setenv("SFB200_SCHED", "halving")
+    p, prog = _program(1)
+    info = p.lowered.launches[0].info
     items = info["work_items_fn"](0, 1024)
     assert items[:148] == [(t, 0, 1024) for t in range(148)]
     rest = items[148:]
@@ -41,12 +67,6 @@ def test_config1_plan(native_lib):
     for t in range(148, 304):
         covered = sorted((p0, p1) for tt, p0, p1 in rest if tt == t)
         assert covered[0][0] == 0 and covered[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
-    steps = sum(p1 - p0 + info["stream_overhead_planes"] for _, p0, p1 in items) / 148.0
-    assert steps <= 1.03 * (19 * 16 * 1024 / 148.0)
-    table = info["work_fn"](0, 1024)
-    assert table[:3] == [0, 0, len(items)] and table[3:9] == [0, 0, 1024, 1, 0, 1024]
-    # algorithmic bytes of a pass: the field in, the field out
-    assert launches[0].reads == ["a"] and launches[0].writes == ["b3"]
 
 
 def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
