@@ -549,7 +549,7 @@ class GroupAnalysis:
                     n += (R if dr is not None else 1) * (V if dc is not None else 1) * per
             per_step = max(per_step, n)
         hoisted += per_step
-        return (live + 2) * R * V * per + 8 + min(12, R * V * per) * len(self.ops) + hoisted
+        return (live + 2) * R * V * per + 8 + min(10, R * V * per) * len(self.ops) + hoisted
 
 
 class Geometry:
@@ -1942,14 +1942,32 @@ def candidate_geometries(program, ops, options):
 # cells).  The compute rate depends on the rows a thread owns (fewer rows = more exchange traffic per
 # cell through shared memory, the co-limiter of the fused kernels) and collapses when the register
 # windows do not fit the register file of the chosen CTA size.
-HBM_BYTES_PER_S = 6.1e12
-UPDATES_PER_S = {4: 2.7e12, 8: 0.95e12}     # computed cell updates per second at R = 4, by element size
+def _measured_hbm_rate():
+    """Bytes per second a streaming kernel can expect: 0.95 of the copy bandwidth the driver measured on this
+    pool (``MEASURED_PEAKS.json``; the hdiff pass sustains 0.97 of it), 6.1 TB/s when that file is absent."""
+    try:
+        import json
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+        with open(path) as f:
+            return 0.95e9 * float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6.1e12
+
+
+HBM_BYTES_PER_S = _measured_hbm_rate()
+# computed cell updates per second (halo cells included) of a fused 3-D pass at R = 4 rows per thread and 8
+# warps, by element size: float32 from the Jacobi-3D chain (1024^3, depth 4, 64x64 tile: 4.25 ms per step)
+UPDATES_PER_S = {4: 2.85e12, 8: 0.95e12}
 UPDATES_PER_S_2D = {4: 2.7e12, 8: 1.95e12}  # 2-D rows, 8-warp CTAs (float64: 16 operators in 9.07 ms, r01c)
-ROW_FACTOR = {1: 0.45, 2: 0.7, 3: 0.85, 4: 1.0, 5: 1.0}
+# rate relative to R = 4 (measured on the same chain, each at the largest CTA its registers allow: R = 3 x 12
+# warps 3.84 ms on a 72x64 tile, R = 2 x 16 warps 4.76 ms; fewer rows = more exchange traffic per cell, but
+# more warps per scheduler to hide it)
+ROW_FACTOR = {1: 0.45, 2: 0.89, 3: 1.05, 4: 1.0, 5: 1.0}
 # 2-D rows: compute rate of a CTA of w warps relative to 8 warps, measured on the float64 chain
 # (profiles/r01c_sweep_config3_small_ctas.txt; tile efficiency factored out): independent small CTAs
 # hide each other's barrier and exchange latency
 SMALL_CTA_FACTOR_2D = {1: 1.03, 2: 1.14, 4: 1.06}
+PREFETCH_FACTOR = {5: 0.97}                 # 3-D passes: modelled time with the TMA ring 5 planes ahead instead of 2
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
 LAUNCH_LATENCY = 2.4e-6                     # a small kernel behind another on one stream (8 launches of 32^3: 19.4 us)
 # one streamed plane step per fused operator when nothing else limits it: barrier + exchange of a CTA, which
@@ -1965,16 +1983,20 @@ def _tile_efficiency(ana, geo):
 
 def modelled_time(program, ops, ana, geo):
     fields = program.fields
-    nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields)
-    nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
     eff = _tile_efficiency(ana, geo)
+    # every tile loads its halo too: the memory system moves the inputs 1 / (tile efficiency) times (the
+    # neighbouring tile's copy mostly comes from L2, but it still has to come)
+    nbytes = sum(fields[i.name].nbytes for i in ana.ext_fields) / eff
+    nbytes += sum(fields[i.name].nbytes for i in ana.fields.values() if i.stored)
     # tiles that stick out of the domain compute cells nobody stores (80 rows under 32-row tiles = 3 tiles)
     nk = program.shape[-1]
     used = nk / float(-(-nk // geo.BK) * geo.BK)
     if ana.ndim == 3:
         nj = program.shape[-2]
         used *= nj / float(-(-nj // geo.BJ) * geo.BJ)
-    t_mem = nbytes / HBM_BYTES_PER_S
+    # a pass bound by HBM needs enough warps in flight to keep the memory system busy (hdiff: 5 warps per
+    # SM reach 0.79 of what 15 warps do)
+    t_mem = nbytes / (HBM_BYTES_PER_S * min(1.0, 0.7 + 0.02 * (geo.NT // 32) * resident_estimate(geo)))
     table = UPDATES_PER_S if ana.ndim == 3 else UPDATES_PER_S_2D
     rate = float(os.environ.get("SFB200_RATE_F{}".format(ana.dtype.bytes * 8), table[ana.dtype.bytes]))
     rate *= ROW_FACTOR.get(geo.R, 1.0) if ana.ndim == 3 else SMALL_CTA_FACTOR_2D.get(geo.NT // 32, 1.0)
@@ -2009,22 +2031,28 @@ def choose_geometry(program, ops, options):
                 continue
             # TMA ring depth - 1: 2 planes ahead by default; 2-D rows are small (a ring of 6 fits many
             # times) and measured fastest with 5 (profiles/r01_sweep_sync_prefetch.txt)
-            prefetch = opts.prefetch or (5 if len(program.shape) == 2 else 2)
+            # 3-D tiles: both ring depths compete -- 5 planes ahead is worth ~3 % (ring depth 6 = the unroll
+            # factor; Jacobi-3D 4.18 -> 4.03 ms) unless the deeper ring costs the tile rows its shared memory
+            # would have held (hdiff: 48 -> 32 rows, 0.162 -> 0.180 ms)
+            prefetches = [opts.prefetch] if opts.prefetch else ([5] if len(program.shape) == 2 else [5, 2])
             explicit = bool(opts.rows_per_thread and opts.warps)
             for (R, WR, WC, KS) in candidates:
-                try:
-                    ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
-                    geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(opts, "sync", "") or DEFAULT_SYNC,
-                                   direct=bool(getattr(opts, "direct", 0)))
-                except NotStreamable:
-                    continue
-                if geo.smem > SMEM_LIMIT:
-                    continue
-                if not explicit and ana.register_estimate(R, V) > register_limit(geo.NT) + REG_SLACK:
-                    continue
-                t = modelled_time(program, ops, ana, geo)
-                if best is None or t < best[0] * (1 - 1e-6):
-                    best = (t, ana, geo)
+                for prefetch in prefetches:
+                    try:
+                        ana = GroupAnalysis(program, ops, exchange_cols=(WC > 1))
+                        geo = Geometry(ana, V, R, WR, WC, prefetch, KS, getattr(opts, "sync", "") or DEFAULT_SYNC,
+                                       direct=bool(getattr(opts, "direct", 0)))
+                    except NotStreamable:
+                        break
+                    if geo.smem > SMEM_LIMIT:
+                        continue
+                    if not explicit and ana.register_estimate(R, V) > register_limit(geo.NT) + REG_SLACK:
+                        continue
+                    t = modelled_time(program, ops, ana, geo)
+                    if len(program.shape) == 3 and len(prefetches) > 1:
+                        t *= PREFETCH_FACTOR.get(prefetch, 1.0)
+                    if best is None or t < best[0] * (1 - 1e-6):
+                        best = (t, ana, geo)
         except NotStreamable:
             continue
     if best is None:

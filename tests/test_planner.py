@@ -69,6 +69,17 @@ def test_config1_halving_list(native_lib, monkeypatch):
         assert covered[0][0] == 0 and covered[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
 
 
+@pytest.mark.parametrize("index", [1, 2, 3])
+def test_cost_model_alone_finds_the_measured_plans(native_lib, monkeypatch, index):
+    """SFB200_TUNED=0: without the table of measured plans the planner's cost model arrives at the same
+    kernels for the three benchmark programs (the table is a record of measurements, not what the choice rests on)."""
+    tuned = _program(index)[0]
+    monkeypatch.setenv("SFB200_TUNED", "0")
+    model = _program(index)[0]
+    assert [l.kernel for l in model.lowered.launches] == [l.kernel for l in tuned.lowered.launches]
+    assert [l.info["tile"] for l in model.lowered.launches] == [l.info["tile"] for l in tuned.lowered.launches]
+
+
 def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
     p, prog = _program(3)
     # 137 column tiles on 4 x 148 CTA slots: fewer tiles than slots, so the plain (tile, chunk) grid is used
