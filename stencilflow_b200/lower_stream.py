@@ -1973,6 +1973,8 @@ LAUNCH_LATENCY = 2.4e-6                     # a small kernel behind another on o
 # one streamed plane step per fused operator when nothing else limits it: barrier + exchange of a CTA, which
 # grows with its warps (12-warp 3-D CTAs: 9 steps of 4 operators on 32^3 in 12 us; 2-warp 2-D CTAs: 0.05 us)
 STEP_LATENCY_PER_WARP = 0.018e-6
+STEP_LATENCY_3D = 0.2e-6
+STREAM_SETUP = 3.0e-6                       # prologue of a streamed kernel before its first plane
 
 
 def _tile_efficiency(ana, geo):
@@ -2008,8 +2010,15 @@ def modelled_time(program, ops, ana, geo):
     overhead = ana.t_end_offset() - ana.t_begin_offset()
     n_stream = program.shape[0]
     steps = overhead + (-(-n_stream * tiles // slots) if tiles >= slots else -(-n_stream // (slots // tiles)))
-    t_lat = steps * STEP_LATENCY_PER_WARP * (geo.NT // 32) * len(ops)
-    return max(t_mem, t_cmp, t_lat) + LAUNCH_LATENCY
+    per_op_step = STEP_LATENCY_PER_WARP * (geo.NT // 32)
+    if ana.ndim == 3:
+        # ... and however few warps: TMA wait, ring loads, the dependent arithmetic and the barrier of one
+        # operator on one plane take ~0.2 us, and a streamed kernel spends ~3 us before its first plane
+        # (barriers, descriptors, the first TMA round trip): 2-warp CTAs on 32^3 run 9 steps of 4 operators
+        # in 14.7 us (ncu), eight one-operator launches of the same program take 24 us in total
+        per_op_step = max(per_op_step, STEP_LATENCY_3D)
+    t_lat = steps * per_op_step * len(ops)
+    return max(t_mem, t_cmp, t_lat) + LAUNCH_LATENCY + STREAM_SETUP
 
 
 def choose_geometry(program, ops, options):
