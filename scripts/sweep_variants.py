@@ -6,7 +6,7 @@ produces bit-identical output (on-device checksum of the program outputs against
 
 A variant is written d<depth>[r<rows>][v<cells>][w<warps>][k<threads per row>][p<prefetch>][s|f][x]
 where a trailing ``s`` selects neighbour-only ("pair") synchronisation, ``f`` per-field mbarriers
-("flags") and ``x`` direct reads of the input's neighbour rows from the TMA ring.  Generator switches
+("flags"), ``h`` two half-CTAs sharing the tile ("halves") and ``x`` direct reads of the input's neighbour rows from the TMA ring.  Generator switches
 read from the environment go in front: ``SFB200_ST64=1,SFB200_SPLITBAR=1:d4r3w12p5``.
 ``--repeat N`` times the list N times round-robin (clock drift hits every variant alike) and reports the
 median; ``--warm`` only compiles (no GPU needed: fills the program cache that travels to the GPU box).
@@ -38,13 +38,13 @@ def parse(text):
         k, v = kv.split("=")
         os.environ[k] = v
         ENV_KEYS.add(k)
-    m = re.fullmatch(r"d(\d+)(?:r(\d+))?(?:v(\d+))?(?:w(\d+))?(?:k(\d+))?(?:p(\d+))?([sf]?)(x?)", text)
+    m = re.fullmatch(r"d(\d+)(?:r(\d+))?(?:v(\d+))?(?:w(\d+))?(?:k(\d+))?(?:p(\d+))?([sfh]?)(x?)", text)
     if not m:
         raise SystemExit("bad variant " + text)
     d, r, v, w, k, p, s, x = m.groups()
     return planner.PlanOptions(max_depth=int(d), rows_per_thread=int(r or 0), vector=int(v or 0),
                                warps=int(w or 0), threads_per_row=int(k or 0), prefetch=int(p or 0),
-                               sync={"s": "pair", "f": "flags"}.get(s, "cta"), direct=1 if x else 0)
+                               sync={"s": "pair", "f": "flags", "h": "halves"}.get(s, "cta"), direct=1 if x else 0)
 
 
 def main():

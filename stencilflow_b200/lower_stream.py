@@ -173,6 +173,25 @@ __device__ __forceinline__ void sf_sync_neighbours(int w) {
         if (w > 0) sf_bar_pair(w);
     }
 }
+// ---- two half-CTAs ("halves" mode) ----
+// The warps of the upper and the lower half of a tile meet at their own 1-per-plane named barrier (ids 1 / 2)
+// and load their own half of every input plane; only the two warps at the seam exchange rows, and they
+// shake hands through producer/consumer barriers: bar.arrive (does not wait) after the step's last ring
+// access, bar.sync on the other half's barrier before the next step.  The halves may therefore run up to a
+// step apart -- when one is in its arithmetic the other can be in its exchange phase -- while sharing the
+// tile (no halo between them, unlike two independent CTAs of half the size).
+__device__ __forceinline__ void sf_bar_half(u32 upper, u32 nthreads) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p bar.sync 2, %1;\n\t@!p bar.sync 1, %1;\n\t}"
+                 ::"r"(upper), "r"(nthreads) : "memory");
+}
+template <int ID_LO, int ID_HI>
+__device__ __forceinline__ void sf_seam_handshake(u32 seam_lo, u32 seam_hi) {
+    // seam_lo: the last warp of the lower half, seam_hi: the first warp of the upper half (warp-uniform)
+    asm volatile("{\n\t.reg .pred pa, pb;\n\tsetp.ne.u32 pa, %0, 0;\n\tsetp.ne.u32 pb, %1, 0;\n\t"
+                 "@pa bar.arrive %2, 64;\n\t@pb bar.arrive %3, 64;\n\t"
+                 "@pa bar.sync %3, 64;\n\t@pb bar.sync %2, 64;\n\t}"
+                 ::"r"(seam_lo), "r"(seam_hi), "n"(ID_LO), "n"(ID_HI) : "memory");
+}
 // ---- packed float32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a) ----
 __device__ __forceinline__ float2 sf_add2(float2 a, float2 b) {
     float2 r;
@@ -619,6 +638,11 @@ class Geometry:
                 self.box = [32 * V, 1]
         if not self.pair:
             self.box = [self.box_cols, self.TR, 1] if ana.ndim == 3 else [self.box_cols, 1]
+        # "halves": two half-CTAs sharing a tile (see sf_bar_half in the prelude)
+        self.halves = bool(sync == "halves" and ana.ndim == 3 and WC == 1 and not self.direct and nw % 2 == 0
+                           and WR % 2 == 0 and self.TC == self.box_cols and (WR // 2) % max(1, 32 // KS) == 0)
+        if self.halves:
+            self.box = [self.box_cols, self.TR // 2, 1]
         self.smem = self._smem(ana)
 
     def _smem(self, ana):
@@ -639,7 +663,7 @@ class Geometry:
                 off += i.col_ring * self.WR * self.WC * 2 * self.R * i.col_reach * b
                 off = (off + 127) & ~127
         self.bar_off = off
-        off += 8 * self.D * (self.NW if self.pair else 1)
+        off += 8 * self.D * (self.NW if self.pair else (2 if self.halves else 1))
         self.item_off = off            # persistent CTAs: the work item thread 0 fetched for everybody
         off += 16
         self.sbar_off = off            # split CTA barrier (see StreamKernelGen.split_barrier)
@@ -714,6 +738,10 @@ class StreamKernelGen:
         # (see _flags_ok); anything else keeps the barrier.
         self.fbar = {}
         self.flags = bool(geo.flags and not geo.pair and self.pipeline and self.U % 2 == 0 and self._flags_ok())
+        if getattr(geo, "halves", False):
+            if self.U % 2:
+                raise NotStreamable("half-CTA synchronisation needs an even unroll factor")
+            self.split_barrier = False
         if self.flags:
             self.split_barrier = False
         self._waited = set()
@@ -909,7 +937,8 @@ class StreamKernelGen:
                     T=T, f=self.fid[i.name], o=g.xcol_off[i.name]))
         e("unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sf_smem + {});".format(g.bar_off))
         e("if (threadIdx.x == 0) {")
-        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(g.D * (g.NW if g.pair else 1)), 2)
+        e("for (int s = 0; s < {}; ++s) sf_mbar_init(&bars[s], 1);".format(
+            g.D * (g.NW if g.pair else (2 if g.halves else 1))), 2)
         if self.split_barrier:
             e("sf_mbar_init(sf_smem + {}, {});".format(g.sbar_off, g.NT // 32), 2)
         for n in range(len(self.fbar) if self.flags else 0):
@@ -1043,6 +1072,21 @@ class StreamKernelGen:
                         dst, n, g.HK0, g.box[0], plane), 2)
             e("};")
             issuers = nwarps
+        elif g.halves:
+            half_bytes = (g.TR // 2) * g.TC * self.ct.bytes
+            e("const u32 upper_u = warp_u >= {} ? 1u : 0u;              // which half of the tile this warp belongs to".format(nwarps // 2))
+            e("const u32 seam_lo = warp_u == {} ? 1u : 0u, seam_hi = warp_u == {} ? 1u : 0u;".format(nwarps // 2 - 1, nwarps // 2))
+            e("unsigned long long* const wbars = bars + upper_u * {};".format(g.D))
+            e("auto issue = [&](int t, int s) {")
+            e("sf_mbar_expect_tx(&wbars[s], {});".format(half_bytes * len(ext)), 2)
+            for n, i in enumerate(ext):
+                plane = "t - ({}) - s_base".format(i.lag)
+                dst = "tile_{f} + s * {sz} + upper_u * {hsz}".format(f=self.fid[i.name], sz=g.TR * g.TC,
+                                                                     hsz=(g.TR // 2) * g.TC)
+                e("sf_tma_load_3d({}, &tm_{}, &wbars[s], tile_k0 - {}, tile_j0 - {} + (int)upper_u * {}, {});".format(
+                    dst, n, g.HK0, g.HJ0, g.TR // 2, plane), 2)
+            e("};")
+            issuers = 0
         else:
             e("unsigned long long* const wbars = bars;")
             e("auto issue = [&](int t, int s) {")
@@ -1065,7 +1109,10 @@ class StreamKernelGen:
                 if issuers > 1:
                     e("}", 2)
             e("};")
-        e("const bool issuer = warp_u < {};".format(issuers))
+        if g.halves:
+            e("const bool issuer = (warp_u % {}) == 0;            // the first warp of each half".format(nwarps // 2))
+        else:
+            e("const bool issuer = warp_u < {};".format(issuers))
         e("if (issuer && sf_elect_one()) {")
         if static_d:
             e("for (int p = 0; p < {}; ++p) if (t_begin + p < t_end) issue(t_begin + p, p);".format(g.P), 2)
@@ -1211,6 +1258,11 @@ class StreamKernelGen:
             last_comm = self._emit_ops(u, ext, ph, self.ops_limit)
             if g.pair:
                 e("sf_sync_neighbours<{}>(warp_u);".format(g.NW), 2)
+            elif g.halves:
+                # (barrier ids alternate with the step so that a half one step ahead cannot arrive twice on one id)
+                ids = (3, 4) if u % 2 == 0 else (5, 6)
+                e("sf_seam_handshake<{}, {}>(seam_lo, seam_hi);".format(*ids), 2)
+                e("sf_bar_half(upper_u, {}u);".format(g.NT // 2), 2)
             elif self.flags:
                 pass
             elif self.split_barrier:
@@ -1272,7 +1324,7 @@ class StreamKernelGen:
         none = (False, [], len(self.ops))
         if a.ndim != 3 or g.WC != 1 or g.pair or os.environ.get("SFB200_HALO_SKIP", HALO_SKIP_DEFAULT) == "0":
             return none
-        if self.flags or self.split_barrier or g.NT % 32 or 32 % g.KS:
+        if self.flags or self.split_barrier or g.halves or g.NT % 32 or 32 % g.KS:
             return none
         gpw = 32 // g.KS
         best = none
@@ -2346,7 +2398,7 @@ def lower_group(lowered: LoweredProgram, ops: List[StencilOp], options, speciali
                               "tile": [geo.TR, geo.TC],
                               "block_out": [geo.BJ, geo.BK], "halo": [geo.HJ0, geo.HJ1, geo.HK0, geo.HK1],
                               "prefetch": geo.P, "persistent": gen.persistent, "peer_push": gen.peer_push,
-                              "tiles": gx * gy, "sync": "pair" if geo.pair else ("flags" if gen.flags else "cta"), "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "halo_skip": [gen.rotate_rows, gen.skip_warps, gen.skip_from], "lags": {n: i.lag for n, i in ana.fields.items()},
+                              "tiles": gx * gy, "sync": "pair" if geo.pair else ("halves" if geo.halves else ("flags" if gen.flags else "cta")), "direct": sorted(geo.direct), "unroll": gen.U, "packed": gen.G == 2, "halo_skip": [gen.rotate_rows, gen.skip_warps, gen.skip_from], "lags": {n: i.lag for n, i in ana.fields.items()},
                               "windows": {n: i.window for n, i in ana.fields.items() if i.consumed},
                               "window_registers": ana.window_registers(geo.R, geo.V),
                               "register_estimate": ana.register_estimate(geo.R, geo.V),

@@ -392,6 +392,9 @@ PAIR_VARIANTS_3D = [
     # read after it was re-published, e.g. the fork/join program)
     (4, 3, 12, 16, 5, "flags"), (4, 4, 8, 16, 2, "flags"), (2, 4, 16, 32, 3, "flags"), (3, 2, 16, 16, 2, "flags"),
     (1, 4, 8, 32, 2, "flags"),
+    # two half-CTAs sharing the tile: own barrier and TMA boxes per half, producer/consumer handshake at the seam
+    (4, 3, 12, 16, 5, "halves"), (4, 4, 8, 16, 2, "halves"), (2, 4, 16, 32, 3, "halves"), (3, 2, 16, 16, 2, "halves"),
+    (1, 4, 8, 32, 2, "halves"),
 ]
 
 
@@ -470,6 +473,9 @@ def test_pair_sync_is_selected_when_asked(native_lib):
     p = CudaProgram(program_path("ref_jacobi3d_32x32x32_8itr_8vec"), allocate=False,
                     plan_options=PlanOptions(max_depth=4, rows_per_thread=3, warps=12, sync="flags"))
     assert all(l.info["sync"] == "flags" for l in p.lowered.launches if l.family == "streamed")
+    p = CudaProgram(program_path("ref_jacobi3d_32x32x32_8itr_8vec"), allocate=False,
+                    plan_options=PlanOptions(max_depth=4, rows_per_thread=3, warps=12, sync="halves"))
+    assert all(l.info["sync"] == "halves" for l in p.lowered.launches if l.family == "streamed")
     # a field that is read through its ring by two operators keeps the CTA barrier
     p = CudaProgram(program_path("fork_join_20x16x24"), allocate=False,
                     plan_options=PlanOptions(max_depth=4, rows_per_thread=3, warps=12, sync="flags"))
@@ -489,7 +495,9 @@ def test_pair_sync_bit_identical_at_scale(gpu, kind):
                     dict(max_depth=4, rows_per_thread=4, warps=8, sync="pair", prefetch=5),
                     dict(max_depth=4, rows_per_thread=3, warps=12, sync="pair", prefetch=3),
                     dict(max_depth=4, rows_per_thread=3, warps=12, sync="flags", prefetch=5),
-                    dict(max_depth=4, rows_per_thread=4, warps=8, sync="flags", prefetch=2)]
+                    dict(max_depth=4, rows_per_thread=4, warps=8, sync="flags", prefetch=2),
+                    dict(max_depth=4, rows_per_thread=3, warps=12, sync="halves", prefetch=5),
+                    dict(max_depth=4, rows_per_thread=4, warps=8, sync="halves", prefetch=2)]
     else:
         prog, out, dt = programs.jacobi2d_chain([3000, 16384], 8), "b7", np.float64
         variants = [dict(max_depth=8, vector=4, warps=8, sync="cta"),
