@@ -760,10 +760,13 @@ class StreamKernelGen:
             persistent = persistent_default(self.n_tiles, SM_COUNT * resident_estimate(geo))
         self.persistent = bool(persistent)
         if self.bc_mode not in ("thread", "cta"):
-            # per-thread fix-ups pay off where domain-edge tiles would hold up the others (many tiles, persistent
-            # CTAs: Jacobi-3D 1024^3 4.17 -> 4.05 ms); their extra code costs registers the kernels with few,
-            # long-running tiles do not have to spare (hdiff: 123 -> 128 registers and a spill, 0.163 -> 0.180 ms)
-            self.bc_mode = "thread" if self.persistent else "cta"
+            # per-thread fix-ups (only warps that own out-of-domain cells enter the code) paid off while
+            # domain-edge tiles could hold up the work list (halving rounds: Jacobi-3D 1024^3 4.17 -> 4.05 ms).
+            # With the longest-first list the edge tiles stream first and the plain per-CTA test -- branch-free,
+            # fewer registers (hdiff: 123 instead of 128 and no spill, 0.163 vs 0.180 ms) -- is the faster one
+            # again (3.79 -> 3.73 ms, profiles/r02_sweep_sync_config1.txt)
+            sched = os.environ.get("SFB200_SCHED", SCHED_DEFAULT)
+            self.bc_mode = "thread" if (self.persistent and sched != "lpt") else "cta"
 
     def _published(self, info):
         return bool((info.row_ring and info.name not in self.geo.direct) or info.col_ring)
