@@ -216,17 +216,18 @@ def make_program(chain) -> StencilProgram:
                 except ValueError:
                     pass
         statements = node.statements
-        # SFB200_REASSOCIATE: "auto" (default) = float32: taps that straddle two packed pairs are summed first
-        # (the float32 kernels compute on pairs of k-neighbours: one issue slot in eight less); float64: the
-        # sums additionally become balanced trees -- a dependent chain of two instead of three additions per
-        # cell, which the latency-bound float64 2-D chain (two warps per scheduler) turns into 2.8 %
-        # (8.01 -> 7.79 ms with the split loops of round 2; it lost 1.2 % before them).  "0": the reference's
-        # left-to-right order; "1": pairing for float32 only; "2" / "3": balanced trees for float32 / float64.
-        # Both kernel families lower from the rewritten tree, so fused and one-operator results stay bit-identical.
+        # SFB200_REASSOCIATE: "auto" (default) = taps that straddle two packed pairs are summed first (the
+        # float32 kernels compute on pairs of k-neighbours: one issue slot in eight less) and sums become
+        # balanced trees -- a dependent chain of two instead of three additions per cell, which the
+        # latency-bound float64 2-D chain (two warps per scheduler) turns into 2.8 % (8.01 -> 7.79 ms with the
+        # split loops of round 2; it lost 1.2 % before them) and the float32 Jacobi-3D pass into 0.8 %
+        # (3.73 -> 3.70 ms).  "0": the reference's left-to-right order; "1": pairing only, float32 only; "2" /
+        # "3": balanced trees for float32 / float64 only.  Both kernel families lower from the rewritten tree,
+        # so fused and one-operator results stay bit-identical.
         mode = os.environ.get("SFB200_REASSOCIATE", "auto")
         is32, is64 = node.data_type == dtypes.float32, node.data_type == dtypes.float64
         if (is32 and mode in ("auto", "1", "2")) or (is64 and mode in ("auto", "3")):
-            balance = (is32 and mode == "2") or is64
+            balance = mode != "1"
             statements = [ex.Statement(st.target, ex.pair_odd_taps(st.value, balance)) for st in statements]
         ops.append(StencilOp(
             name=node.name, shape=shape, iterators=iterators, accesses=accesses,
