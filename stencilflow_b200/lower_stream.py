@@ -766,7 +766,7 @@ class StreamKernelGen:
             # fewer registers (hdiff: 123 instead of 128 and no spill, 0.163 vs 0.180 ms) -- is the faster one
             # again (3.79 -> 3.73 ms, profiles/r02_sweep_sync_config1.txt)
             sched = os.environ.get("SFB200_SCHED", SCHED_DEFAULT)
-            self.bc_mode = "thread" if (self.persistent and sched != "lpt") else "cta"
+            self.bc_mode = "thread" if (self.persistent and sched not in ("lpt", "rows")) else "cta"
 
     def _published(self, info):
         return bool((info.row_ring and info.name not in self.geo.direct) or info.col_ring)
@@ -2254,8 +2254,8 @@ def schedule_work(n_tiles, n_planes, slots, overhead, edge_tiles=None):
       tile-minor so that the CTAs of a round hold adjacent tiles of one range; the last items are short
       (a few times the warm-up), which bounds how far apart the CTAs finish."""
     mode = os.environ.get("SFB200_SCHED", SCHED_DEFAULT)
-    if mode == "lpt" and edge_tiles is not None and n_tiles >= 2 * slots:
-        return _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles)
+    if mode in ("lpt", "rows") and edge_tiles is not None and n_tiles >= 2 * slots:
+        return _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles, by_rows=(mode == "rows"))
     whole = int((n_tiles / float(slots)) / (1.0 + EDGE_SLOWDOWN)) * slots
     items = [(t, 0, n_planes) for t in range(whole)]
     tiles = n_tiles - whole
@@ -2289,7 +2289,7 @@ def schedule_work(n_tiles, n_planes, slots, overhead, edge_tiles=None):
     return items
 
 
-def _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles):
+def _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles, by_rows=False):
     """Alternative list for passes with at least two tiles per slot: every full wave of tiles streams whole
     (one warm-up per tile), the *domain-edge tiles first* -- they are the slow ones, and the CTAs that drew
     them simply fetch their next tile later (longest-processing-time-first) -- and only the tiles that do not
@@ -2297,6 +2297,13 @@ def _schedule_longest_first(n_tiles, n_planes, slots, overhead, edge_tiles):
     edge = [t for t in range(n_tiles) if t in edge_tiles]
     inner = [t for t in range(n_tiles) if t not in edge_tiles]
     order = edge + inner
+    if by_rows:
+        # (experiment) keep the tiles in index order -- whole tile rows side by side, better halo sharing in
+        # L2 -- and only bring the runs of edge tiles at both ends of the index range to the front
+        first_inner = next((t for t in range(n_tiles) if t not in edge_tiles), 0)
+        last_inner = max([t for t in range(n_tiles) if t not in edge_tiles] + [0])
+        head = list(range(0, first_inner)) + list(range(last_inner + 1, n_tiles))
+        order = head + list(range(first_inner, last_inner + 1))
     whole = (n_tiles // slots) * slots
     items = [(t, 0, n_planes) for t in order[:whole]]
     rest = order[whole:]
