@@ -376,6 +376,9 @@ def _cuda_program_base():
     return CudaProgram
 
 
+PEER_PUSH_DEFAULT = "0"
+
+
 class SlabProgram:
     """A stencil program executed on this rank's slab.  Same execution interface as ``CudaProgram``
     (``execute``, ``launch_count``, ``plan``, ``buffers`` ...) plus slab-aware upload/download."""
@@ -389,9 +392,12 @@ class SlabProgram:
         chain = KernelChainGraph(stencil_file)
         if plan_options is None:
             plan_options = planner.PlanOptions()
-        # streamed passes push their edge planes into the neighbours' halos themselves (SFB200_PEER_PUSH=0:
-        # peer copies on the communication streams for every launch, the path one-operator kernels take)
-        plan_options.peer_push = comm.world > 1 and os.environ.get("SFB200_PEER_PUSH", "1") != "0"
+        # how the edge planes of a streamed pass reach the neighbours' halos: peer copies on the communication
+        # streams behind the launch (default, the path one-operator kernels take too), or SFB200_PEER_PUSH=1:
+        # the kernel stores them itself after each segment.  The in-kernel push overlaps the transfer with the
+        # rest of the pass, but its kernel variant runs 6-15 % slower than the plain one (same loop, a less
+        # lucky register assignment: 4.21-4.57 vs 3.96 ms per step at N = 4, profiles/r02d_push_kinds.txt)
+        plan_options.peer_push = comm.world > 1 and os.environ.get("SFB200_PEER_PUSH", PEER_PUSH_DEFAULT) != "0"
         probe = planner.plan_program(make_program(chain), options=plan_options)
         axis = probe.lowered.slab_axis
         if axis is None:

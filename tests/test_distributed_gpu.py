@@ -60,9 +60,13 @@ def _results(out):
     ("upwind3d_fwd_24x16x32_4st", True),           # one-sided reach: rank 0 only receives, rank 1 only sends
     ("upwind3d_fwd_24x16x32_4st", False),
     ("upwind3d_bwd_20x12x32_5st_f64", True),
-    ("ref_jacobi3d_32x32x32_8itr_8vec:copy", True),    # SFB200_PEER_PUSH=0: copy pushes for streamed passes too
+    ("ref_jacobi3d_32x32x32_8itr_8vec:copy", True),    # SFB200_PEER_PUSH=0 (the default): copy pushes for streamed passes too
     ("upwind3d_fwd_24x16x32_4st:copy", True),
-    ("chain3d:160x64x128:d2", True),                    # 4 passes, ping-pong storage, in-kernel pushes
+    ("chain3d:160x64x128:d2", True),                    # 4 passes, ping-pong storage
+    ("ref_jacobi3d_32x32x32_8itr_8vec:kernel", True),  # SFB200_PEER_PUSH=1: the streamed kernels push their edge planes themselves
+    ("upwind3d_fwd_24x16x32_4st:kernel", True),
+    ("chain3d:160x64x128:d2:kernel", True),
+    ("jacobi3d_24x20x40_4itr_shrink_f64:kernel", True),
 ])
 def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if _gpu_count(native_lib) < 2:
@@ -78,6 +82,9 @@ def test_two_gpus_match_oracle_and_single_gpu(native_lib, name, fuse):
     if name.endswith(":copy"):
         name = name[:-len(":copy")]
         env["SFB200_PEER_PUSH"] = "0"
+    if name.endswith(":kernel"):
+        name = name[:-len(":kernel")]
+        env["SFB200_PEER_PUSH"] = "1"
     if name.endswith(":d2"):
         name = name[:-len(":d2")]
         env["SFB200_MAX_DEPTH"] = "2"
