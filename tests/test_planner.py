@@ -80,6 +80,25 @@ def test_cost_model_alone_finds_the_measured_plans(native_lib, monkeypatch, inde
     assert [l.info["tile"] for l in model.lowered.launches] == [l.info["tile"] for l in tuned.lowered.launches]
 
 
+def test_pipelined_call_pieces_are_short_at_both_ends():
+    """The overlapped host-array call: short pieces at both ends (what cannot overlap is the first upload and the
+    last download), equal pieces in between, every plane exactly once."""
+    from stencilflow_b200.cuda_program import CudaProgram
+    for (n0, n1, pieces, reach) in [(0, 1024, 16, 4), (0, 32768, 16, 8), (100, 612, 8, 2), (0, 80, 16, 1), (0, 2048, 32, 4)]:
+        ends = CudaProgram._piece_ends(n0, n1, pieces, reach)
+        sizes = [b - a for a, b in zip([n0] + ends[:-1], ends)]
+        assert ends[-1] == n1 and all(s_ > 0 for s_ in sizes) and ends == sorted(ends)
+        if (n1 - n0) // pieces > 8 * reach:
+            assert sizes[0] == max(4 * reach, 8) == sizes[-1] and sizes[0] < max(sizes)
+            assert sizes[1] == 2 * sizes[0] == sizes[-2] and sizes == sizes[::-1][:len(sizes)] or sum(sizes) == n1 - n0
+            assert sum(1 for s_ in sizes if s_ >= max(sizes) - 1) >= pieces // 2
+    os.environ["SFB200_PIPELINE_RAMP"] = "0"
+    try:
+        assert CudaProgram._piece_ends(0, 1024, 16, 4) == [64 * (s_ + 1) for s_ in range(16)]
+    finally:
+        del os.environ["SFB200_PIPELINE_RAMP"]
+
+
 def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
     p, prog = _program(3)
     # 137 column tiles on 4 x 148 CTA slots: fewer tiles than slots, so the plain (tile, chunk) grid is used
@@ -119,12 +138,17 @@ def test_one_cta_per_tile_chunk_grid_still_available(native_lib, monkeypatch):
     assert (gx, gy) == (19, 16) and gx * gy * gz >= 4 * 148
 
 
-def test_schedule_work_covers_every_plane_once():
+@pytest.mark.parametrize("sched", ["lpt", "rows", "halving"])
+def test_schedule_work_covers_every_plane_once(monkeypatch, sched):
     from stencilflow_b200.lower_stream import schedule_work, pack_work_table
+    monkeypatch.setenv("SFB200_SCHED", sched)
     for (tiles, planes, slots, ov) in [(304, 1024, 148, 8), (1184, 256, 148, 8), (150, 1024, 148, 8), (1, 32, 148, 8),
                                        (24, 1024, 148, 5), (137, 32768, 592, 16), (3, 7, 148, 2), (600, 64, 148, 8),
-                                       (304, 64, 148, 8), (2, 1024, 148, 8), (1184, 2048, 148, 8)]:
-        items = schedule_work(tiles, planes, slots, ov)
+                                       (304, 64, 148, 8), (2, 1024, 148, 8), (1184, 2048, 148, 8), (296, 1024, 148, 8),
+                                       (297, 40, 148, 8)]:
+        # (domain-edge tiles as the lowering passes them: a frame around a 19-wide grid of tiles)
+        edge = {t for t in range(tiles) if t % 19 in (0, 18) or t < 19 or t >= tiles - 19}
+        items = schedule_work(tiles, planes, slots, ov, edge_tiles=edge)
         seen = {}
         for (t, p0, p1) in items:
             assert 0 <= t < tiles and 0 <= p0 < p1 <= planes
