@@ -519,6 +519,31 @@ def test_pair_sync_bit_identical_at_scale(gpu, kind):
     assert all(s_[1] == sums[0][1] for s_ in sums[1:]), sums
 
 
+GENERATOR_SWITCHES = [
+    {"SFB200_SPLITBAR": "1"}, {"SFB200_HALO_SKIP": "1"}, {"SFB200_ST64": "5"}, {"SFB200_SPLITLOOP": "1"},
+    {"SFB200_SPLITLOOP": "0"}, {"SFB200_BC_MODE": "thread"}, {"SFB200_BC_MODE": "cta", "SFB200_SCHED": "halving"},
+    {"SFB200_UNROLL": "12", "SFB200_UNROLL_MULT": "2"}, {"SFB200_REASSOCIATE": "0"}, {"SFB200_L2HINT": "0"},
+]
+
+
+@pytest.mark.parametrize("switches", GENERATOR_SWITCHES, ids=lambda d: ",".join("{}={}".format(k[7:], v) for k, v in d.items()))
+@pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "jacobi3d_16x24x32_5itr_const1",
+                                  "jacobi2d_96x128_6itr_shrink_f64"])
+def test_generator_switches_match_oracle(gpu, name, switches, monkeypatch):
+    """The code-shape switches of DESIGN section 11 (measured alternatives the defaults were chosen against) stay
+    correct: fused passes under each of them against the oracle."""
+    from oracle import reference_numpy as rn
+    from stencilflow_b200.planner import PlanOptions
+    for k, v in switches.items():
+        monkeypatch.setenv(k, v)
+    inputs = random_inputs(name, seed=41)
+    expected = rn.run_reference(program_path(name), inputs)
+    opts = PlanOptions(max_depth=4, rows_per_thread=3, warps=12) if "3d" in name else PlanOptions(max_depth=6, vector=4, warps=2)
+    got, prog = _run_cuda(name, inputs, opts)
+    assert any(l.family == "streamed" for l in prog.lowered.launches)
+    _check(name, got, expected)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["ref_jacobi3d_32x32x32_8itr_8vec", "hdiff_24x28x16", "fork_join_20x16x24",
                                   "jacobi2d_96x128_6itr_shrink_f64", "lowdim3d_20x24x48_3st_f32"])
