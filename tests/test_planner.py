@@ -106,9 +106,12 @@ def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
     assert not l.info["persistent"]
     gx, gy, gz = l.grid_fn(0, 32768)
     assert gx == 137 and gy == 1
+    # many short chunks (at most 32 x the 16 warm-up rows each: measured 4.7 % faster than the 30 long chunks
+    # that minimise waves x (rows + warm-up)), the last wave of CTAs nearly full
     waves = gx * gz / (4 * 148.0)
-    assert waves >= 4 and (waves - int(waves) > 0.85 or waves == int(waves))
-    assert l.info["stream_overhead_planes"] * gz <= 0.03 * 32768
+    assert waves >= 12 and (waves - int(waves) > 0.85 or waves == int(waves))
+    assert l.info["chunk_fn"](0, 32768) <= 32 * l.info["stream_overhead_planes"]
+    assert l.info["stream_overhead_planes"] * gz <= 0.04 * 32768
     # ... unless persistent CTAs are forced
     monkeypatch.setenv("SFB200_PERSISTENT", "1")
     p, prog = _program(3)
