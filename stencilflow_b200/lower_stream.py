@@ -1984,7 +1984,7 @@ def candidate_geometries(program, ops, options):
     else:
         # 2-D rows: the warps of a CTA sit side by side; small CTAs (2-4 warps) let several independent
         # CTAs share an SM, each with its own barrier and TMA ring
-        for w in ([options.warps] if options.warps else [2, 4, 8, 16]):
+        for w in ([options.warps] if options.warps else [1, 2, 4, 8, 16]):
             out.append((1, 1, w, 32))
     ks = getattr(options, "threads_per_row", 0)
     if ks:
@@ -2019,9 +2019,10 @@ UPDATES_PER_S_2D = {4: 2.7e12, 8: 1.95e12}  # 2-D rows, 8-warp CTAs (float64: 16
 # more warps per scheduler to hide it)
 ROW_FACTOR = {1: 0.45, 2: 0.89, 3: 1.05, 4: 1.0, 5: 1.0}
 # 2-D rows: compute rate of a CTA of w warps relative to 8 warps, measured on the float64 chain
-# (profiles/r01c_sweep_config3_small_ctas.txt; tile efficiency factored out): independent small CTAs
-# hide each other's barrier and exchange latency
-SMALL_CTA_FACTOR_2D = {1: 1.03, 2: 1.14, 4: 1.06}
+# (profiles/r01c_sweep_config3_small_ctas.txt, re-measured with the short chunks of round 2,
+# profiles/r02_sweep_sync_config3.txt: 1 / 2 / 4 warps 6.60 / 7.50 / 7.44 ms; tile efficiency factored out):
+# independent small CTAs that start at different times hide each other's barrier and exchange latency
+SMALL_CTA_FACTOR_2D = {1: 1.39, 2: 1.14, 4: 1.11}
 PREFETCH_FACTOR = {5: 0.97}                 # 3-D passes: modelled time with the TMA ring 5 planes ahead instead of 2
 GENERAL_EFFICIENCY = 0.84                   # fraction of HBM bandwidth the one-operator kernel reaches
 LAUNCH_LATENCY = 2.4e-6                     # a small kernel behind another on one stream (8 launches of 32^3: 19.4 us)

@@ -101,34 +101,31 @@ def test_pipelined_call_pieces_are_short_at_both_ends():
 
 def test_config3_plan_uses_small_independent_ctas(native_lib, monkeypatch):
     p, prog = _program(3)
-    # 137 column tiles on 4 x 148 CTA slots: fewer tiles than slots, so the plain (tile, chunk) grid is used
-    l = p.lowered.launches[0]
-    assert not l.info["persistent"]
-    gx, gy, gz = l.grid_fn(0, 32768)
-    assert gx == 137 and gy == 1
-    # many short chunks (at most 32 x the 16 warm-up rows each: measured 4.7 % faster than the 30 long chunks
-    # that minimise waves x (rows + warm-up)), the last wave of CTAs nearly full
-    waves = gx * gz / (4 * 148.0)
-    assert waves >= 12 and (waves - int(waves) > 0.85 or waves == int(waves))
-    assert l.info["chunk_fn"](0, 32768) <= 32 * l.info["stream_overhead_planes"]
-    assert l.info["stream_overhead_planes"] * gz <= 0.04 * 32768
-    # ... unless persistent CTAs are forced
-    monkeypatch.setenv("SFB200_PERSISTENT", "1")
-    p, prog = _program(3)
     launches = p.lowered.launches
     assert [len(l.ops) for l in launches] == [8, 8]
     l = launches[0]
-    assert l.block == (64, 1, 1) and l.info["tile"] == [1, 256] and l.info["prefetch"] == 5
-    # four 2-warp CTAs share an SM (255 registers each): fewer tiles (137) than slots (592), so every tile is
-    # cut into row ranges -- four long ones first, then ever shorter ones; warm-up rows stay a small part
-    assert l.info["tiles"] == 137
-    items = l.info["work_items_fn"](0, 32768, 4 * 148)
-    assert l.grid_fn(0, 32768, 4 * 148) == (4 * 148, 1, 1) and len(items) >= 4 * 4 * 148
-    assert [t for t, _, _ in items[:137]] == list(range(137))          # tile-minor: neighbours side by side
+    # one-warp CTAs, eight of them per SM (255 registers each), each with its own TMA ring and barrier
+    assert l.block == (32, 1, 1) and l.info["tile"] == [1, 128] and l.info["prefetch"] == 5
+    # 293 column tiles on 8 x 148 CTA slots: fewer tiles than slots, so the plain (tile, chunk) grid is used
+    assert not l.info["persistent"] and l.info["tiles"] == 293
+    gx, gy, gz = l.grid_fn(0, 32768)
+    assert gx == 293 and gy == 1
+    # many short chunks (at most 32 x the 16 warm-up rows each: measured 4.7 % faster than the few long chunks
+    # that minimise waves x (rows + warm-up)), the last wave of CTAs nearly full
+    waves = gx * gz / (8 * 148.0)
+    assert waves >= 12 and (waves - int(waves) > 0.8 or waves == int(waves))
+    assert l.info["chunk_fn"](0, 32768) <= 32 * l.info["stream_overhead_planes"]
+    assert l.info["stream_overhead_planes"] * gz <= 0.04 * 32768
+    # ... unless persistent CTAs are forced: every tile cut into row ranges, long ones first
+    monkeypatch.setenv("SFB200_PERSISTENT", "1")
+    p, prog = _program(3)
+    l = p.lowered.launches[0]
+    items = l.info["work_items_fn"](0, 32768, 8 * 148)
+    assert l.info["persistent"] and l.grid_fn(0, 32768, 8 * 148) == (min(8 * 148, len(items)), 1, 1)
+    assert [t for t, _, _ in items[:293]] == list(range(293))          # tile-minor: neighbours side by side
     rows = sorted((p0, p1) for (t, p0, p1) in items if t == 5)
     assert rows[0][0] == 0 and rows[-1][1] == 32768 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
     overhead = l.info["stream_overhead_planes"]
-    assert overhead * len(rows) <= 0.03 * 32768
     assert min(p1 - p0 for p0, p1 in rows) >= 4 * overhead
 
 
@@ -179,7 +176,7 @@ def test_cost_model_picks_small_ctas_and_depth_for_untuned_2d(native_lib):
     p, prog = _program(3, "w1d")                      # not in the table of measured plans
     launches = p.lowered.launches
     assert [len(l.ops) for l in launches] == [8, 8]
-    assert launches[0].block == (64, 1, 1) and launches[0].info["prefetch"] == 5
+    assert launches[0].block == (32, 1, 1) and launches[0].info["prefetch"] == 5     # one-warp CTAs, eight per SM
     assert "w" in launches[0].reads                   # the 1-D weight is read by the fused pass itself
 
 
