@@ -80,6 +80,20 @@ def test_cost_model_alone_finds_the_measured_plans(native_lib, monkeypatch, inde
     assert [l.info["tile"] for l in model.lowered.launches] == [l.info["tile"] for l in tuned.lowered.launches]
 
 
+def test_launch_bound_grids_are_not_fused(native_lib, tmp_path):
+    """The latency terms of the cost model: on 32^3 ... 64^3 an 8-operator chain is eight one-operator launches
+    (replayed through a CUDA graph), from 96^3 on it is fused passes (profiles/r02b_small_grid_sizes.txt)."""
+    import json
+    from stencilflow_b200 import programs
+    from stencilflow_b200.cuda_program import CudaProgram
+    for n, fused in ((32, False), (64, False), (96, True), (256, True)):
+        path = tmp_path / "chain_{}.json".format(n)
+        path.write_text(json.dumps(programs.jacobi3d_chain([n, n, n], 8)))
+        p = CudaProgram(str(path), allocate=False)
+        families = [l.family for l in p.lowered.launches]
+        assert (families == ["streamed", "streamed"]) if fused else (families == ["general"] * 8), (n, families)
+
+
 def test_pipelined_call_pieces_are_short_at_both_ends():
     """The overlapped host-array call: short pieces at both ends (what cannot overlap is the first upload and the
     last download), equal pieces in between, every plane exactly once."""
